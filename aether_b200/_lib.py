@@ -1,0 +1,123 @@
+"""ctypes binding of libaether_b200.so (the C ABI declared in include/aether_b200.h).
+
+The product path has NO fallback: if the library is missing or a call returns a non-zero status a
+RuntimeError is raised.  PyTorch is used by callers only for device memory and streams; this module
+passes raw device pointers (`tensor.data_ptr()`) and the current CUDA stream handle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+_LIB_PATH = Path(__file__).resolve().parent / "lib" / "libaether_b200.so"
+_lib = None
+
+STATUS = {0: "AETHER_OK", 1: "AETHER_ERR_INVALID", 2: "AETHER_ERR_CUDA", 3: "AETHER_ERR_WORKSPACE"}
+
+c_void_p, c_int32, c_int64, c_float, c_double = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double
+
+
+class DitConfig(C.Structure):
+    _fields_ = [("num_heads", c_int32), ("head_dim", c_int32), ("num_layers", c_int32),
+                ("in_channels", c_int32), ("out_channels", c_int32), ("patch_size", c_int32),
+                ("time_embed_dim", c_int32), ("text_embed_dim", c_int32), ("flip_sin_to_cos", c_int32),
+                ("freq_shift", c_float), ("norm_eps", c_float), ("ff_mult", c_int32)]
+
+
+class DitLayerWeights(C.Structure):
+    _fields_ = [(n, c_void_p) for n in (
+        "w_qkv", "b_qkv", "w_out", "b_out", "w_ff1", "b_ff1", "w_ff2", "b_ff2",
+        "norm1_g", "norm1_b", "norm2_g", "norm2_b", "qn_g", "qn_b", "kn_g", "kn_b")]
+
+
+class DitWeights(C.Structure):
+    _fields_ = [(n, c_void_p) for n in (
+        "w_time1", "b_time1", "w_time2", "b_time2", "w_text", "b_text", "w_patch", "b_patch",
+        "w_adaln", "b_adaln", "normf_g", "normf_b", "normo_g", "normo_b", "w_proj", "b_proj",
+        "pos_embedding")] + [("layers", C.POINTER(DitLayerWeights))]
+
+
+class DpmCoeffs(C.Structure):
+    _fields_ = [("sqrt_alpha", c_float), ("sqrt_one_minus_alpha", c_float), ("m1", c_float), ("m2", c_float),
+                ("m3", c_float), ("m4", c_float), ("m_noise", c_float), ("second_order", c_int32),
+                ("prediction_type", c_int32)]
+
+
+# name -> (restype, argtypes); every symbol include/aether_b200.h declares.
+SIGNATURES = {
+    "aether_abi_version": (c_int32, []),
+    "aether_device_ok": (c_int32, []),
+    "aether_gemm_bf16": (C.c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_int32,
+                                   c_void_p, c_int32, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p]),
+    "aether_attention_bf16": (C.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_float, c_void_p]),
+    "aether_ln_modulate": (C.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p,
+                                     c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                     c_void_p]),
+    "aether_qk_norm_rope": (C.c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_float, c_void_p, c_void_p, c_void_p]),
+    "aether_small_m_linear": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
+                                        c_void_p]),
+    "aether_timestep_sinusoid": (C.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_float, c_void_p]),
+    "aether_patchify": (C.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "aether_unpatchify": (C.c_int, [c_void_p, c_int64, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                    c_void_p]),
+    "aether_add_pos_embed": (C.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
+    "aether_dit_create": (C.c_int, [C.POINTER(DitConfig), C.POINTER(DitWeights), C.POINTER(c_void_p)]),
+    "aether_dit_destroy": (None, [c_void_p]),
+    "aether_dit_workspace_bytes": (c_int64, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32]),
+    "aether_dit_forward": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
+                                     c_int32, c_int32, c_int32, c_int32, c_void_p, c_int64, c_int32, c_void_p]),
+    "aether_cfg_dpm_step": (C.c_int, [c_void_p, c_int32, c_int32, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
+                                      C.POINTER(DpmCoeffs), c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "aether_scale_reduce": (C.c_int, [c_void_p, c_int32, c_int64, c_void_p, c_int32, c_int64, c_int64, c_int64,
+                                      c_void_p, c_void_p]),
+    "aether_blend_crossfade": (C.c_int, [c_void_p, c_int64, c_void_p, c_int32, c_int64, c_void_p, c_int32, c_int64,
+                                         c_double, c_int64, c_int64, c_int64, c_int32, c_int64, c_void_p]),
+    "aether_scale_copy": (C.c_int, [c_void_p, c_int64, c_void_p, c_int32, c_int64, c_double, c_int32, c_int64,
+                                    c_int64, c_void_p]),
+}
+
+
+def lib_path() -> Path:
+    return _LIB_PATH
+
+
+def load():
+    """Load the library (once).  Raises RuntimeError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists():
+        raise RuntimeError(
+            f"{_LIB_PATH} not found: the aether_b200 CUDA extension is not built. "
+            "Run `python -m aether_b200.build` (or __graft_entry__.build()). There is no CPU fallback.")
+    lib = C.CDLL(str(_LIB_PATH), mode=getattr(os, "RTLD_NOW", 2))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)        # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str):
+    if status != 0:
+        raise RuntimeError(f"aether_b200: {what} failed with status {status} ({STATUS.get(status, '?')})")
+
+
+def ptr(t) -> int:
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return 0 if t is None else t.data_ptr()
+
+
+def current_stream() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_device():
+    lib = load()
+    if not lib.aether_device_ok():
+        raise RuntimeError("aether_b200 needs an sm_100 (B200) CUDA device; none is visible. No CPU fallback exists.")
+    return lib

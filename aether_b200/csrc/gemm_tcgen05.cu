@@ -1,0 +1,315 @@
+// K3/K4: bf16 GEMM  C[M,N] = epi(A[M,K] * W[N,K]^T)  on 5th-gen tensor cores.
+//
+// Replaces every nn.Linear of CogVideoXBlock (to_q/k/v fused, to_out, ff.net.0.proj, ff.net.2) plus
+// patch_embed.proj / text_proj / proj_out -- the third-party modules the reference calls at
+// aether/pipelines/aetherv1_pipeline_cogvideox.py:865-875.
+//
+// Design (one CTA per SM, persistent over output tiles):
+//   warp 0      : TMA producer   - cp.async.bulk.tensor 128B-swizzled {64 x 128} A and {64 x 256} W boxes
+//                                  into a 4-stage shared-memory ring (48 KB / stage)
+//   warp 1      : MMA issuer     - one elected thread issues tcgen05.mma.cta_group::1.kind::f16
+//                                  (M=128, N=256, K=16) x4 per stage, accumulating fp32 in TMEM
+//   warps 2..5  : epilogue       - tcgen05.ld the 128x256 fp32 tile (double-buffered: 2 x 256 TMEM columns,
+//                                  so the epilogue of tile i overlaps the main loop of tile i+1), apply
+//                                  bias / GELU-tanh / gate*x+residual, pack to bf16, stage a 128x64 chunk
+//                                  in swizzled shared memory and TMA-store it.
+// Roofline: tensor (2*M*N*K flop / launch); operands are re-read from L2, HBM traffic ~ (M*K + N*K + M*N)*2 B.
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace aether {
+
+namespace gemm {
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2;
+constexpr int B_BYTES = BN * BK * 2;
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int CCHUNK = 64;                       // epilogue column chunk (64 bf16 = one 128B swizzle row)
+constexpr int C_BYTES = BM * CCHUNK * 2;
+constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 2 * C_BYTES + 256;
+constexpr int THREADS = 192;
+constexpr int GROUP_M = 8;
+
+struct Params {
+  int M, N, K;
+  int num_m, num_n;
+  const float* bias;        // [N] or null
+  const float* gate_vid;    // EPI 2: [B, N] (batch stride gate_bstride) for rows s >= St
+  const float* gate_txt;    // EPI 2: same for rows s < St
+  int64_t gate_bstride;
+  int S, St;                // row -> (b = row / S, s = row % S)
+  __nv_bfloat16* C;         // EPI 2 reads the residual from C (in place)
+  int64_t ldc;
+};
+
+__device__ __forceinline__ void tile_coords(int t, const Params& p, int& m_blk, int& n_blk) {
+  const int group_size = GROUP_M * p.num_n;
+  const int g = t / group_size;
+  const int first_m = g * GROUP_M;
+  const int gm = min(GROUP_M, p.num_m - first_m);
+  const int local = t - g * group_size;
+  m_blk = first_m + local % gm;
+  n_blk = local / gm;
+}
+
+__device__ __forceinline__ float gelu_tanh(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  float inner = k0 * (x + k1 * x * x * x);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(inner));
+  return 0.5f * x * (1.0f + t);
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+            const __grid_constant__ CUtensorMap tmap_c, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_c = smem + STAGES * STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + 2 * C_BYTES);
+  uint64_t* full = bars;                    // [STAGES]
+  uint64_t* empty = bars + STAGES;          // [STAGES]
+  uint64_t* tmem_full = bars + 2 * STAGES;  // [2]
+  uint64_t* tmem_empty = tmem_full + 2;     // [2]
+  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.num_m * p.num_n;
+  const int num_kb = (p.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    tma_prefetch_desc(&tmap_c);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_base_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        int m_blk, n_blk;
+        tile_coords(t, p, m_blk, n_blk);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          uint8_t* sb = sa + A_BYTES;
+          mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
+          tma_load_2d(sa, &tmap_a, &full[stage], kb * BK, m_blk * BM);
+          tma_load_2d(sb, &tmap_b, &full[stage], kb * BK, n_blk * BN);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint64_t a_desc = make_sw128_desc(sa);
+          const uint64_t b_desc = make_sw128_desc(sa + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // +32 bytes (encoded >>4 = 2) per K=16 step inside the 128B swizzle atom
+            tc_mma_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(&empty[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        tc_commit(&tmem_full[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..5, 128 threads)
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int row_in_tile = q * 32 + lane;
+    const bool store_leader = (threadIdx.x == 64);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int cbuf = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      int m_blk, n_blk;
+      tile_coords(t, p, m_blk, n_blk);
+      const int row = m_blk * BM + row_in_tile;
+      const bool row_ok = row < p.M;
+      const float* gate = nullptr;
+      if (EPI == 2) {
+        const int b = row_ok ? row / p.S : 0;
+        const int s = row_ok ? row - b * p.S : 0;
+        gate = (s < p.St ? p.gate_txt : p.gate_vid) + b * p.gate_bstride;
+      }
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int ch = 0; ch < BN / CCHUNK; ++ch) {
+        const int n0 = n_blk * BN + ch * CCHUNK;
+        if (n0 >= p.N) break;
+        uint32_t v0[32], v1[32];
+        const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * BN + ch * CCHUNK;
+        tmem_ld_32x32b_x32(taddr, v0);
+        tmem_ld_32x32b_x32(taddr + 32, v1);
+        tc_wait_ld();
+
+        uint32_t packed[32];
+#pragma unroll
+        for (int g8 = 0; g8 < 8; ++g8) {     // 8 groups of 8 columns (one 16-byte bf16 vector each)
+          float x[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int c = g8 * 8 + j;
+            x[j] = __uint_as_float(c < 32 ? v0[c] : v1[c - 32]);
+          }
+          const int n = n0 + g8 * 8;
+          const bool col_ok = n < p.N;       // N % 8 == 0 is required
+          if (p.bias != nullptr && col_ok) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
+            x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
+            x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+          }
+          if (EPI == 1) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = gelu_tanh(x[j]);
+          }
+          if (EPI == 2) {
+            if (row_ok && col_ok) {
+              const float4 g0 = __ldg(reinterpret_cast<const float4*>(gate + n));
+              const float4 g1 = __ldg(reinterpret_cast<const float4*>(gate + n + 4));
+              const uint4 r = *reinterpret_cast<const uint4*>(p.C + int64_t(row) * p.ldc + n);
+              x[0] = bf16_lo(r.x) + g0.x * x[0]; x[1] = bf16_hi(r.x) + g0.y * x[1];
+              x[2] = bf16_lo(r.y) + g0.z * x[2]; x[3] = bf16_hi(r.y) + g0.w * x[3];
+              x[4] = bf16_lo(r.z) + g1.x * x[4]; x[5] = bf16_hi(r.z) + g1.y * x[5];
+              x[6] = bf16_lo(r.w) + g1.z * x[6]; x[7] = bf16_hi(r.w) + g1.w * x[7];
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) packed[g8 * 4 + j] = pack_bf16x2(x[2 * j], x[2 * j + 1]);
+        }
+        // staging buffer `cbuf` was last used two chunks ago; make sure that TMA store has read it
+        if (store_leader) tma_store_wait_read<1>();
+        named_bar_sync(1, 128);
+        uint8_t* crow = smem_c + cbuf * C_BYTES + row_in_tile * 128;
+#pragma unroll
+        for (int c16 = 0; c16 < 8; ++c16) {
+          const int phys = c16 ^ (row_in_tile & 7);
+          *reinterpret_cast<uint4*>(crow + phys * 16) =
+              make_uint4(packed[c16 * 4], packed[c16 * 4 + 1], packed[c16 * 4 + 2], packed[c16 * 4 + 3]);
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (store_leader) {
+          tma_store_2d(&tmap_c, smem_c + cbuf * C_BYTES, n0, m_blk * BM);
+          tma_store_commit();
+        }
+        cbuf ^= 1;
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+    if (store_leader) tma_store_wait<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+template <int EPI>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const Params& p, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    AETHER_CUDA_OK(cudaFuncSetAttribute(gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles = p.num_m * p.num_n;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  gemm_kernel<EPI><<<grid, THREADS, SMEM_BYTES, stream>>>(ta, tb, tc, p);
+  AETHER_CUDA_OK(cudaGetLastError());
+  return AETHER_OK;
+}
+}  // namespace gemm
+
+int gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int M, int N, int K,
+              const float* bias, int epilogue, const float* gate_vid, const float* gate_txt, int64_t gate_bstride,
+              int S, int St, cudaStream_t stream) {
+  AETHER_CHECK_ARG(M > 0 && N > 0 && K > 0);
+  AETHER_CHECK_ARG(N % 8 == 0 && K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldc % 8 == 0);
+  AETHER_CHECK_ARG(epilogue >= 0 && epilogue <= 2);
+  AETHER_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(C) & 15) == 0);
+  if (epilogue == 2) AETHER_CHECK_ARG(gate_vid != nullptr && gate_txt != nullptr && S > 0);
+  CUtensorMap ta, tb, tc;
+  int rc;
+  if ((rc = make_tmap_2d(&ta, A, M, K, lda, gemm::BM, gemm::BK))) return rc;
+  if ((rc = make_tmap_2d(&tb, W, N, K, ldw, gemm::BN, gemm::BK))) return rc;
+  if ((rc = make_tmap_2d(&tc, C, M, N, ldc, gemm::BM, gemm::CCHUNK))) return rc;
+  gemm::Params p;
+  p.M = M; p.N = N; p.K = K;
+  p.num_m = (int)ceil_div(M, gemm::BM);
+  p.num_n = (int)ceil_div(N, gemm::BN);
+  p.bias = bias;
+  p.gate_vid = gate_vid; p.gate_txt = gate_txt; p.gate_bstride = gate_bstride;
+  p.S = S > 0 ? S : M; p.St = St;
+  p.C = reinterpret_cast<__nv_bfloat16*>(C);
+  p.ldc = ldc;
+  switch (epilogue) {
+    case 0: return gemm::launch<0>(ta, tb, tc, p, stream);
+    case 1: return gemm::launch<1>(ta, tb, tc, p, stream);
+    default: return gemm::launch<2>(ta, tb, tc, p, stream);
+  }
+}
+
+}  // namespace aether
+
+extern "C" int aether_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc,
+                                int32_t M, int32_t N, int32_t K, const float* bias, int32_t epilogue,
+                                const float* gate_vid, const float* gate_txt, int64_t gate_bstride, int32_t S,
+                                int32_t St, void* stream) {
+  return aether::gemm_bf16(A, lda, W, ldw, C, ldc, M, N, K, bias, epilogue, gate_vid, gate_txt, gate_bstride, S, St,
+                           reinterpret_cast<cudaStream_t>(stream));
+}

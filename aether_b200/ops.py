@@ -1,0 +1,145 @@
+"""Per-kernel Python entry points: torch tensors in, C-ABI calls out (no torch compute on this path).
+
+Each function mirrors one `aether_*` symbol of include/aether_b200.h and validates dtype/contiguity
+before passing raw pointers.  Used by the module wrappers (transformer.py, scheduler.py, ...) and by
+the parity tests, which call the CUDA path through exactly this boundary.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import check, current_stream, ptr
+
+BF16, F32, F64 = torch.bfloat16, torch.float32, torch.float64
+
+
+def _need(t: torch.Tensor, dtype, name: str):
+    if t.dtype != dtype or not t.is_cuda or not t.is_contiguous():
+        raise ValueError(f"{name}: expected contiguous CUDA {dtype}, got {t.dtype} cuda={t.is_cuda} "
+                         f"contiguous={t.is_contiguous()}")
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, epilogue: int = 0,
+         out: Optional[torch.Tensor] = None, gate_vid=None, gate_txt=None, S: int = 0, St: int = 0) -> torch.Tensor:
+    """out[M,N] = epi(a[M,K] @ w[N,K]^T).  epilogue 2 updates `out` in place (out = out + gate * (acc + bias))."""
+    lib = _lib.require_device()
+    _need(a, BF16, "a"); _need(w, BF16, "w")
+    M, K = a.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty(M, N, dtype=BF16, device=a.device)
+    _need(out, BF16, "out")
+    gb = 0
+    if epilogue == 2:
+        _need(gate_vid, F32, "gate_vid"); _need(gate_txt, F32, "gate_txt")
+        gb = gate_vid.stride(0) if gate_vid.dim() == 2 else N
+    if bias is not None:
+        _need(bias, F32, "bias")
+    check(lib.aether_gemm_bf16(ptr(a), a.stride(0), ptr(w), w.stride(0), ptr(out), out.stride(0), M, N, K, ptr(bias),
+                               epilogue, ptr(gate_vid), ptr(gate_txt), gb, S, St, current_stream()), "gemm_bf16")
+    return out
+
+
+def attention(qkv: torch.Tensor, scale: Optional[float] = None) -> torch.Tensor:
+    """qkv [B,S,3,H,64] bf16 -> out [B,S,H*64] bf16."""
+    lib = _lib.require_device()
+    _need(qkv, BF16, "qkv")
+    B, S, three, H, dh = qkv.shape
+    assert three == 3 and dh == 64
+    out = torch.empty(B, S, H * dh, dtype=BF16, device=qkv.device)
+    check(lib.aether_attention_bf16(ptr(qkv), ptr(out), B, S, H, float(scale if scale is not None else dh ** -0.5),
+                                    current_stream()), "attention_bf16")
+    return out
+
+
+def ln_modulate(x, gamma, beta, eps, shift_vid, scale_vid, shift_txt=None, scale_txt=None, St=0, gamma2=None,
+                beta2=None, mod_bstride=None, out=None):
+    """x [B,S,D] bf16; shift/scale fp32 [B,D] (or views with batch stride mod_bstride)."""
+    lib = _lib.require_device()
+    _need(x, BF16, "x")
+    B, S, D = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    if mod_bstride is None:
+        mod_bstride = shift_vid.stride(0) if shift_vid.dim() == 2 else D
+    check(lib.aether_ln_modulate(ptr(x), ptr(out), B, S, St, D, ptr(gamma), ptr(beta), float(eps), ptr(gamma2),
+                                 ptr(beta2), ptr(shift_vid), ptr(scale_vid), ptr(shift_txt), ptr(scale_txt),
+                                 mod_bstride, current_stream()), "ln_modulate")
+    return out
+
+
+def qk_norm_rope(qkv, gq, bq, gk, bk, eps=1e-6, cos=None, sin=None, St=0):
+    lib = _lib.require_device()
+    _need(qkv, BF16, "qkv")
+    B, S, _, H, _ = qkv.shape
+    for t in (gq, bq, gk, bk):
+        _need(t, F32, "qk norm param")
+    if cos is not None:
+        _need(cos, F32, "cos"); _need(sin, F32, "sin")
+        assert cos.shape == (S - St, 64)
+    check(lib.aether_qk_norm_rope(ptr(qkv), B, S, St, H, ptr(gq), ptr(bq), ptr(gk), ptr(bk), float(eps), ptr(cos),
+                                  ptr(sin), current_stream()), "qk_norm_rope")
+    return qkv
+
+
+def small_m_linear(x, w, bias=None, act=0):
+    lib = _lib.require_device()
+    _need(x, F32, "x"); _need(w, BF16, "w")
+    Bn, K = x.shape
+    N = w.shape[0]
+    y = torch.empty(Bn, N, dtype=F32, device=x.device)
+    check(lib.aether_small_m_linear(ptr(x), ptr(w), ptr(bias), ptr(y), Bn, N, K, act, current_stream()),
+          "small_m_linear")
+    return y
+
+
+def timestep_sinusoid(t, dim, flip_sin_to_cos=True, freq_shift=0.0):
+    lib = _lib.require_device()
+    _need(t, torch.int64, "timesteps")
+    emb = torch.empty(t.shape[0], dim, dtype=F32, device=t.device)
+    check(lib.aether_timestep_sinusoid(ptr(t), ptr(emb), t.shape[0], dim, int(flip_sin_to_cos), float(freq_shift),
+                                       current_stream()), "timestep_sinusoid")
+    return emb
+
+
+def patchify(x):
+    lib = _lib.require_device()
+    _need(x, BF16, "x")
+    B, F, Cc, H, W = x.shape
+    out = torch.empty(B * F * (H // 2) * (W // 2), Cc * 4, dtype=BF16, device=x.device)
+    check(lib.aether_patchify(ptr(x), ptr(out), B, F, Cc, H, W, current_stream()), "patchify")
+    return out
+
+
+def unpatchify(tok, B, F, Cc, H, W):
+    lib = _lib.require_device()
+    _need(tok, BF16, "tok")
+    out = torch.empty(B, F, Cc, H, W, dtype=BF16, device=tok.device)
+    check(lib.aether_unpatchify(ptr(tok), tok.stride(0), ptr(out), B, F, Cc, H, W, current_stream()), "unpatchify")
+    return out
+
+
+def dpm_coeffs(sqrt_alpha, sqrt_one_minus_alpha, m1, m2, m3, m4, m_noise, second_order, prediction_type=0):
+    z = lambda v: 0.0 if v is None else float(v)
+    return _lib.DpmCoeffs(z(sqrt_alpha), z(sqrt_one_minus_alpha), z(m1), z(m2), z(m3), z(m4), z(m_noise),
+                          int(second_order), int(prediction_type))
+
+
+def cfg_dpm_step(model_out, sample, coeffs, noise1, noise2=None, old_x0=None, guidance=1.0, want_prev_f32=False):
+    """model_out [n_cfg, ...] bf16 or fp32; sample bf16 -> (prev_bf16, prev_f32 | None, x0_f32)."""
+    lib = _lib.require_device()
+    _need(sample, BF16, "sample"); _need(noise1, BF16, "noise1")
+    N = sample.numel()
+    n_cfg = model_out.numel() // N
+    assert model_out.numel() == n_cfg * N and n_cfg in (1, 2) and model_out.is_contiguous()
+    prev = torch.empty_like(sample)
+    prev32 = torch.empty(sample.shape, dtype=F32, device=sample.device) if want_prev_f32 else None
+    x0 = torch.empty(sample.shape, dtype=F32, device=sample.device)
+    check(lib.aether_cfg_dpm_step(ptr(model_out), int(model_out.dtype == F32), n_cfg, float(guidance), ptr(sample),
+                                  ptr(old_x0), ptr(noise1), ptr(noise2), C.byref(coeffs), ptr(prev), ptr(prev32),
+                                  ptr(x0), N, current_stream()), "cfg_dpm_step")
+    return prev, prev32, x0

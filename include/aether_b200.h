@@ -1,0 +1,183 @@
+/* aether_b200 -- C ABI of the B200-native Aether denoising hot path.
+ *
+ * The reference (InternRobotics/Aether) has no FFI: its seam is constructor injection of three module
+ * objects into a diffusers pipeline (aether/pipelines/aetherv1_pipeline_cogvideox.py:274-288).  Each entry
+ * point below replaces the device work behind one of those objects' methods and is what a binding for that
+ * method calls (INTEGRATION.md shows the ctypes stubs):
+ *
+ *   aether_dit_forward            <- transformer(hidden_states, encoder_hidden_states, timestep, ofs,
+ *                                    image_rotary_emb, ...)[0]            pipeline :865-875
+ *   aether_cfg_dpm_step           <- CFG combine :895-899 + scheduler.step(...) :907-915 + bf16 cast :916
+ *   aether_vae_*                  <- vae.encode(x).latent_dist / vae.decode(z).sample   :557-620, :931, :936
+ *   aether_scale_reduce / aether_blend_crossfade
+ *                                 <- compute_scale (aether/utils/postprocess_utils.py:847-864) and the
+ *                                    linear cross-fade of evaluation/video_depth/launch_aether.py:166-285
+ *   aether_gemm_bf16, aether_attention_bf16, aether_ln_modulate, ...   the per-kernel entry points the
+ *                                    above are composed of; exported so each kernel can be parity-tested and
+ *                                    profiled in isolation.
+ *
+ * Conventions: every function returns an int status (AETHER_OK = 0) and never throws; all data pointers are
+ * DEVICE pointers owned by the caller; shapes are explicit; `stream` is a cudaStream_t passed as void*;
+ * no function allocates device memory or synchronises the device; handles are re-entrant per handle and
+ * one handle belongs to one GPU.  bf16 tensors are `uint16_t`-sized elements (no torch types anywhere).
+ */
+#ifndef AETHER_B200_H_
+#define AETHER_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AETHER_OK 0
+#define AETHER_ERR_INVALID 1   /* bad argument (shape, alignment, null pointer) */
+#define AETHER_ERR_CUDA 2      /* CUDA runtime / driver error (message on stderr) */
+#define AETHER_ERR_WORKSPACE 3 /* workspace too small */
+
+#define AETHER_ABI_VERSION 1
+int32_t aether_abi_version(void);
+/* 1 when a CUDA device of compute capability 10.x is present, else 0 (never throws). */
+int32_t aether_device_ok(void);
+
+/* ---------------------------------------------------------------- dense contractions (tcgen05) */
+
+/* C[M,N] = epi(A[M,K] . W[N,K]^T), all bf16 row-major, fp32 accumulate in TMEM.
+ *   epilogue 0: + bias        1: gelu_tanh(+ bias)       2: C = C + gate[b, n] * (acc + bias)   (in place)
+ * For epilogue 2 row r belongs to batch b = r / S, token s = r % S; tokens s < St use gate_txt, others
+ * gate_vid (both fp32 [B, N] with batch stride gate_bstride elements).
+ * Replaces nn.Linear inside CogVideoXBlock / CogVideoXPatchEmbed / proj_out (pipeline :865). */
+int aether_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int32_t M,
+                     int32_t N, int32_t K, const float* bias, int32_t epilogue, const float* gate_vid,
+                     const float* gate_txt, int64_t gate_bstride, int32_t S, int32_t St, void* stream);
+
+/* out[B,S,H*64] = softmax(Q K^T * softmax_scale) V over qkv[B,S,3,H,64] (bf16), non-causal, head_dim 64.
+ * Replaces F.scaled_dot_product_attention in CogVideoXAttnProcessor2_0 (pipeline :865). */
+int aether_attention_bf16(const void* qkv, void* out, int32_t B, int32_t S, int32_t H, float softmax_scale,
+                          void* stream);
+
+/* ---------------------------------------------------------------- bandwidth-bound DiT kernels */
+
+/* y[r,:] = LN(x[r,:]; gamma, beta, eps) * (1 + scale[b,:]) + shift[b,:]   (CogVideoXLayerNormZero / AdaLayerNorm)
+ * x, y bf16 [B*S, D]; gamma/beta fp32 [D] (nullable = no affine); shift/scale fp32 with batch stride
+ * mod_bstride; text rows (s < St) use the *_txt vectors.  If gamma2 != NULL a second LayerNorm(gamma2, beta2)
+ * is applied to the result of the first before modulation (norm_final followed by norm_out.norm). */
+int aether_ln_modulate(const void* x, void* y, int32_t B, int32_t S, int32_t St, int32_t D, const float* gamma,
+                       const float* beta, float eps, const float* gamma2, const float* beta2,
+                       const float* shift_vid, const float* scale_vid, const float* shift_txt,
+                       const float* scale_txt, int64_t mod_bstride, void* stream);
+
+/* In place on qkv[B,S,3,H,64]: q,k <- LayerNorm_64(q,k; eps) (affine gq/bq, gk/bk fp32[64]); then for tokens
+ * s >= St the interleaved-pair RoPE with cos/sin fp32 [S-St, 64].  (attn.norm_q/norm_k + apply_rotary_emb) */
+int aether_qk_norm_rope(void* qkv, int32_t B, int32_t S, int32_t St, int32_t H, const float* gq, const float* bq,
+                        const float* gk, const float* bk, float eps, const float* cos, const float* sin,
+                        void* stream);
+
+/* y[b,n] = sum_k act(x[b,k]) * W[n,k] + bias[n];  x fp32 [B,K] (B <= 8), W bf16 [N,K], y fp32 [B,N].
+ * act: 0 identity, 1 SiLU.  Used for the timestep MLP and all AdaLN-Zero linears of a step in one launch. */
+int aether_small_m_linear(const float* x, const void* W, const float* bias, float* y, int32_t B, int32_t N,
+                          int32_t K, int32_t act, void* stream);
+
+/* emb[b, :] = [cos(t_b * f_i) | sin(t_b * f_i)] (flip_sin_to_cos) or [sin | cos];  fp32 [B, dim]. */
+int aether_timestep_sinusoid(const int64_t* timesteps, float* emb, int32_t B, int32_t dim, int32_t flip_sin_to_cos,
+                             float freq_shift, void* stream);
+
+/* patches[(b,f,y,x), c*p*p + dy*p + dx] = in[b,f,c,p*y+dy,p*x+dx]   (bf16; p == 2) */
+int aether_patchify(const void* in, void* patches, int32_t B, int32_t F, int32_t C, int32_t H, int32_t W,
+                    void* stream);
+/* out[b,f,c,2y+dy,2x+dx] = tok[(b,f,y,x), c*4 + dy*2 + dx]   (bf16; tok row stride ld_tok elements) */
+int aether_unpatchify(const void* tok, int64_t ld_tok, void* out, int32_t B, int32_t F, int32_t C, int32_t H,
+                      int32_t W, void* stream);
+/* x[b, s, :] += pos[s, :]   (bf16 [B,S,D] += bf16 [S,D]; learned / sincos positional table) */
+int aether_add_pos_embed(void* x, const void* pos, int32_t B, int32_t S, int32_t D, void* stream);
+
+/* ---------------------------------------------------------------- the DiT forward (handle API) */
+
+typedef struct AetherDitConfig {
+  int32_t num_heads, head_dim, num_layers;
+  int32_t in_channels, out_channels, patch_size;
+  int32_t time_embed_dim, text_embed_dim;
+  int32_t flip_sin_to_cos;
+  float freq_shift, norm_eps;
+  int32_t ff_mult;
+} AetherDitConfig;
+
+typedef struct AetherDitLayerWeights {
+  const void* w_qkv;  const float* b_qkv;    /* [3D, D] bf16 (to_q | to_k | to_v), [3D] */
+  const void* w_out;  const float* b_out;    /* [D, D], [D] */
+  const void* w_ff1;  const float* b_ff1;    /* [ff_mult*D, D] */
+  const void* w_ff2;  const float* b_ff2;    /* [D, ff_mult*D] */
+  const float* norm1_g; const float* norm1_b;  /* [D] (nullable) */
+  const float* norm2_g; const float* norm2_b;
+  const float* qn_g; const float* qn_b; const float* kn_g; const float* kn_b;   /* [head_dim] */
+} AetherDitLayerWeights;
+
+typedef struct AetherDitWeights {
+  const void* w_time1; const float* b_time1;   /* [T, D] bf16, [T] */
+  const void* w_time2; const float* b_time2;   /* [T, T] */
+  const void* w_text;  const float* b_text;    /* [D, text_embed_dim] */
+  const void* w_patch; const float* b_patch;   /* [D, in_channels*p*p] */
+  /* all AdaLN linears concatenated row-wise: per layer [norm1.linear (6D) | norm2.linear (6D)], then
+   * norm_out.linear (2D):  [(12*L + 2) * D, T] bf16 and its bias */
+  const void* w_adaln; const float* b_adaln;
+  const float* normf_g; const float* normf_b;  /* norm_final */
+  const float* normo_g; const float* normo_b;  /* norm_out.norm */
+  const void* w_proj;  const float* b_proj;    /* [p*p*out_channels, D] */
+  const void* pos_embedding;                   /* optional bf16 [St + Sv, D] added after patch embed, or NULL */
+  const AetherDitLayerWeights* layers;         /* [num_layers] host array */
+} AetherDitWeights;
+
+typedef struct AetherDit AetherDit;
+
+int aether_dit_create(const AetherDitConfig* cfg, const AetherDitWeights* w, AetherDit** out);
+void aether_dit_destroy(AetherDit* h);
+/* bytes of scratch the forward needs for batch B, F latent frames of HxW (latent pixels), St text tokens */
+int64_t aether_dit_workspace_bytes(const AetherDit* h, int32_t B, int32_t F, int32_t H, int32_t W, int32_t St);
+/* hidden [B,F,Cin,H,W] bf16; text [B,St,text_dim] bf16; timesteps int64 [B]; cos/sin fp32 [F*(H/p)*(W/p), hd]
+ * (nullable = no RoPE); out [B,F,Cout,H,W] bf16.  n_layers < 0 runs all layers (>= 0: first n, for profiling). */
+int aether_dit_forward(AetherDit* h, const void* hidden, const void* text, const int64_t* timesteps,
+                       const float* rope_cos, const float* rope_sin, void* out, int32_t B, int32_t F, int32_t H,
+                       int32_t W, int32_t St, void* workspace, int64_t workspace_bytes, int32_t n_layers,
+                       void* stream);
+
+/* ---------------------------------------------------------------- scheduler step (K8) */
+
+typedef struct AetherDpmCoeffs {
+  float sqrt_alpha, sqrt_one_minus_alpha;   /* v-prediction -> x0 */
+  float m1, m2, m3, m4, m_noise;            /* DPM-Solver++(2M) SDE multipliers (scheduling_dpm_cogvideox.get_mult) */
+  int32_t second_order;                     /* 0: first-order return (old_x0 NULL or last step) */
+  int32_t prediction_type;                  /* 0 = v_prediction, 1 = epsilon */
+} AetherDpmCoeffs;
+
+/* model_out: bf16 [n_cfg, N] (n_cfg 1 or 2: uncond first, cond second) or fp32 if model_out_fp32;
+ * guidance: u + g (c - u) in fp32.  sample bf16 [N]; old_x0 fp32 [N] or NULL; noise1/noise2 bf16 [N].
+ * Outputs: prev_bf16 [N] (nullable), prev_f32 [N] (nullable), x0_f32 [N].  Rounding follows torch type
+ * promotion in the reference (coef * bf16 tensor rounds to bf16 before the fp32 combine). */
+int aether_cfg_dpm_step(const void* model_out, int32_t model_out_fp32, int32_t n_cfg, float guidance,
+                        const void* sample, const float* old_x0, const void* noise1, const void* noise2,
+                        const AetherDpmCoeffs* c, void* prev_bf16, float* prev_f32, float* x0_f32, int64_t N,
+                        void* stream);
+
+/* ---------------------------------------------------------------- sliding-window blend (K10) */
+
+/* All three work on 2-D views (rows x cols, row stride in ELEMENTS) of disparity buffers that are fp32 (a
+ * raw pipeline window) or fp64 (an already blended accumulation; the reference's np.ones(float64) result).
+ *
+ * aether_scale_reduce: out[0] += sum(f32(p)*f32(t)), out[1] += sum(f32(p)*f32(p)); out is fp64[2], zeroed by
+ *   the caller; scale = out[0]/out[1] (0 when out[1] == 0) is compute_scale (postprocess_utils.py:847-864).
+ * aether_blend_crossfade: dst = acc * w + (scale*win) * (1-w), w = np.linspace(1,0,n_weights)[k] with
+ *   k = column (axis_outer = 0) or row / inner (axis_outer = 1)      (launch_aether.py:217-250, :281-284)
+ * aether_scale_copy: dst = apply_scale ? scale*src : src, widened to fp64   (launch_aether.py:220-227, :277-280) */
+int aether_scale_reduce(const void* pred, int32_t pred_is_f64, int64_t pred_rs, const void* target,
+                        int32_t target_is_f64, int64_t target_rs, int64_t rows, int64_t cols, double* out,
+                        void* stream);
+int aether_blend_crossfade(double* dst, int64_t dst_rs, const void* acc, int32_t acc_is_f64, int64_t acc_rs,
+                           const void* win, int32_t win_is_f64, int64_t win_rs, double scale, int64_t rows,
+                           int64_t cols, int64_t inner, int32_t axis_outer, int64_t n_weights, void* stream);
+int aether_scale_copy(double* dst, int64_t dst_rs, const void* src, int32_t src_is_f64, int64_t src_rs, double scale,
+                      int32_t apply_scale, int64_t rows, int64_t cols, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AETHER_B200_H_ */
