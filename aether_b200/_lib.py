@@ -65,6 +65,7 @@ SIGNATURES = {
     "aether_add_pos_embed": (C.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
     "aether_dit_create": (C.c_int, [C.POINTER(DitConfig), C.POINTER(DitWeights), C.POINTER(c_void_p)]),
     "aether_dit_destroy": (None, [c_void_p]),
+    "aether_dit_set_pos_embedding": (C.c_int, [c_void_p, c_void_p]),
     "aether_dit_workspace_bytes": (c_int64, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32]),
     "aether_dit_forward": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
                                      c_int32, c_int32, c_int32, c_int32, c_void_p, c_int64, c_int32, c_void_p]),

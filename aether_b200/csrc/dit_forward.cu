@@ -106,6 +106,12 @@ extern "C" void aether_dit_destroy(AetherDit* h) {
   delete h;
 }
 
+extern "C" int aether_dit_set_pos_embedding(AetherDit* h, const void* pos_bf16) {
+  if (!h) return AETHER_ERR_INVALID;
+  h->w.pos_embedding = pos_bf16;
+  return AETHER_OK;
+}
+
 extern "C" int64_t aether_dit_workspace_bytes(const AetherDit* h, int32_t B, int32_t F, int32_t H, int32_t W,
                                               int32_t St) {
   if (!h || B <= 0 || F <= 0 || H <= 0 || W <= 0 || St < 0) return -1;

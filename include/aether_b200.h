@@ -131,6 +131,9 @@ typedef struct AetherDit AetherDit;
 
 int aether_dit_create(const AetherDitConfig* cfg, const AetherDitWeights* w, AetherDit** out);
 void aether_dit_destroy(AetherDit* h);
+/* attach / detach (NULL) the additive positional table bf16 [St+Sv, D] used by the next forwards
+ * (CogVideoXPatchEmbed learned / sin-cos branch); the buffer stays owned by the caller. */
+int aether_dit_set_pos_embedding(AetherDit* h, const void* pos_bf16);
 /* bytes of scratch the forward needs for batch B, F latent frames of HxW (latent pixels), St text tokens */
 int64_t aether_dit_workspace_bytes(const AetherDit* h, int32_t B, int32_t F, int32_t H, int32_t W, int32_t St);
 /* hidden [B,F,Cin,H,W] bf16; text [B,St,text_dim] bf16; timesteps int64 [B]; cos/sin fp32 [F*(H/p)*(W/p), hd]
