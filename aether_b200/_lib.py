@@ -71,12 +71,13 @@ SIGNATURES = {
                                      c_int32, c_int32, c_int32, c_int32, c_void_p, c_int64, c_int32, c_void_p]),
     "aether_cfg_dpm_step": (C.c_int, [c_void_p, c_int32, c_int32, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
                                       C.POINTER(DpmCoeffs), c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
-    "aether_scale_reduce": (C.c_int, [c_void_p, c_int32, c_int64, c_void_p, c_int32, c_int64, c_int64, c_int64,
-                                      c_void_p, c_void_p]),
-    "aether_blend_crossfade": (C.c_int, [c_void_p, c_int64, c_void_p, c_int32, c_int64, c_void_p, c_int32, c_int64,
-                                         c_double, c_int64, c_int64, c_int64, c_int32, c_int64, c_void_p]),
-    "aether_scale_copy": (C.c_int, [c_void_p, c_int64, c_void_p, c_int32, c_int64, c_double, c_int32, c_int64,
-                                    c_int64, c_void_p]),
+    "aether_scale_reduce": (C.c_int, [c_void_p, c_int32, c_int64, c_int64, c_void_p, c_int32, c_int64, c_int64,
+                                      c_int64, c_int64, c_int64, c_void_p, c_void_p]),
+    "aether_blend_crossfade": (C.c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int32, c_int64, c_int64, c_void_p,
+                                         c_int32, c_int64, c_int64, c_double, c_int64, c_int64, c_int64, c_int32,
+                                         c_void_p]),
+    "aether_scale_copy": (C.c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int32, c_int64, c_int64, c_double,
+                                    c_int32, c_int64, c_int64, c_int64, c_void_p]),
 }
 
 

@@ -215,9 +215,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Params p) {
         for (int c = 0; c < 128; ++c)
           if (c >= kv_valid) s[c] = 0xFF800000u;   // -inf: TMA zero-filled keys must not contribute
       }
-      float m_tile = __uint_as_float(s[0]);
+      // 8 independent max chains (only 2 softmax warps per scheduler: dependent-chain latency is exposed)
+      float mx[8];
 #pragma unroll
-      for (int c = 1; c < 128; ++c) m_tile = fmaxf(m_tile, __uint_as_float(s[c]));
+      for (int c = 0; c < 8; ++c) mx[c] = __uint_as_float(s[c]);
+#pragma unroll
+      for (int c = 8; c < 128; ++c) mx[c & 7] = fmaxf(mx[c & 7], __uint_as_float(s[c]));
+      const float m_tile =
+          fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])));
       const float m_new = fmaxf(m_used, m_tile);
       const bool need = (m_new - m_used) > rescale_thresh;     // true on the first tile (m_used = -inf)
       if (__any_sync(0xffffffffu, need)) {
@@ -239,17 +244,19 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Params p) {
         }
       }
       const float neg_m = -m_used * sl2;
-      float sum0 = 0.f, sum1 = 0.f;
+      float sum[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) sum[c] = 0.f;
       uint32_t pk[64];
 #pragma unroll
       for (int c = 0; c < 128; c += 2) {
         const float p0 = fast_exp2(fmaf(__uint_as_float(s[c]), sl2, neg_m));
         const float p1 = fast_exp2(fmaf(__uint_as_float(s[c + 1]), sl2, neg_m));
-        sum0 += p0;
-        sum1 += p1;
+        sum[c & 7] += p0;
+        sum[(c + 1) & 7] += p1;
         pk[c >> 1] = pack_bf16x2(p0, p1);
       }
-      l += sum0 + sum1;
+      l += ((sum[0] + sum[1]) + (sum[2] + sum[3])) + ((sum[4] + sum[5]) + (sum[6] + sum[7]));
       {
         const uint32_t(&p0)[32] = *reinterpret_cast<const uint32_t(*)[32]>(&pk[0]);
         const uint32_t(&p1)[32] = *reinterpret_cast<const uint32_t(*)[32]>(&pk[32]);

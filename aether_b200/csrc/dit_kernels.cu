@@ -22,6 +22,13 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
                     pack_bf16x2(f[6], f[7]));
 }
+// 8 consecutive fp32 parameters as two 16-byte loads (p must be 32-byte aligned: all callers index at
+// multiples of 8 floats from cudaMalloc'ed / D-strided vectors).
+__device__ __forceinline__ void load8(const float* __restrict__ p, float (&f)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
 
 // ------------------------------------------------------------------------------------------------
 // K2: LayerNorm (+ optional second LayerNorm) + AdaLN modulation.  One warp per row, the row lives in
@@ -64,11 +71,15 @@ ln_modulate_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restric
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     const int c = (i * 32 + lane) * 8;
+    if (gamma != nullptr) {
+      float gm[8], bt[8];
+      load8(gamma + c, gm);
+      load8(beta + c, bt);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float t = (v[i][j] - mean) * rstd;
-      if (gamma != nullptr) t = t * gamma[c + j] + beta[c + j];
-      v[i][j] = t;
+      for (int j = 0; j < 8; ++j) v[i][j] = (v[i][j] - mean) * rstd * gm[j] + bt[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[i][j] = (v[i][j] - mean) * rstd;
     }
   }
   if (gamma2 != nullptr) {   // second LayerNorm over the (fp32) result of the first
@@ -90,17 +101,22 @@ ln_modulate_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restric
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int c = (i * 32 + lane) * 8;
+      float gm[8], bt[8];
+      load8(gamma2 + c, gm);
+      load8(beta2 + c, bt);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[i][j] = (v[i][j] - mean) * rstd * gamma2[c + j] + beta2[c + j];
+      for (int j = 0; j < 8; ++j) v[i][j] = (v[i][j] - mean) * rstd * gm[j] + bt[j];
     }
   }
   uint4* yr = reinterpret_cast<uint4*>(y + int64_t(row) * D);
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     const int c = (i * 32 + lane) * 8;
-    float o[8];
+    float o[8], sc[8], sh[8];
+    load8(scale + c, sc);
+    load8(shift + c, sh);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = v[i][j] * (1.0f + scale[c + j]) + shift[c + j];
+    for (int j = 0; j < 8; ++j) o[j] = v[i][j] * (1.0f + sc[j]) + sh[j];
     yr[i * 32 + lane] = pack8(o);
   }
 }
@@ -124,9 +140,19 @@ int ln_modulate(const void* x, void* y, int B, int S, int St, int D, const float
     case 2: LAUNCH(2); break;
     case 4: LAUNCH(4); break;
     case 8: LAUNCH(8); break;
+    case 3: LAUNCH(3); break;
+    case 5: LAUNCH(5); break;
+    case 6: LAUNCH(6); break;
+    case 7: LAUNCH(7); break;
+    case 9: LAUNCH(9); break;
+    case 10: LAUNCH(10); break;
+    case 11: LAUNCH(11); break;
     case 12: LAUNCH(12); break;
+    case 13: LAUNCH(13); break;
+    case 14: LAUNCH(14); break;
+    case 15: LAUNCH(15); break;
     case 16: LAUNCH(16); break;
-    default: AETHER_CHECK_ARG(!"unsupported D (need D/256 in {1,2,4,8,12,16})");
+    default: AETHER_CHECK_ARG(!"unsupported D (need D % 256 == 0 and D <= 4096)");
   }
 #undef LAUNCH
   AETHER_CUDA_OK(cudaGetLastError());
@@ -173,13 +199,21 @@ qk_norm_rope_kernel(__nv_bfloat16* __restrict__ qkv, int S, int St, int H, const
   const float* g = is_k ? gk : gq;
   const float* bt = is_k ? bk : bq;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) f[j] = (f[j] - mean) * rstd * g[sub * 8 + j] + bt[sub * 8 + j];
+  for (int j = 0; j < 8; ++j) f[j] = (f[j] - mean) * rstd;
+  {
+    float gm[8], bb[8];
+    load8(g + sub * 8, gm);
+    load8(bt + sub * 8, bb);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = f[j] * gm[j] + bb[j];
+  }
   if (cosb != nullptr && s >= St) {
     // upstream rounds LayerNorm's output to bf16 before apply_rotary_emb upcasts it again
 #pragma unroll
     for (int j = 0; j < 8; ++j) f[j] = __bfloat162float(__float2bfloat16_rn(f[j]));
-    const float* c = cosb + int64_t(s - St) * 64 + sub * 8;
-    const float* sn = sinb + int64_t(s - St) * 64 + sub * 8;
+    float c[8], sn[8];
+    load8(cosb + int64_t(s - St) * 64 + sub * 8, c);
+    load8(sinb + int64_t(s - St) * 64 + sub * 8, sn);
 #pragma unroll
     for (int j = 0; j < 8; j += 2) {
       const float xr = f[j], xi = f[j + 1];

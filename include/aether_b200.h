@@ -163,22 +163,25 @@ int aether_cfg_dpm_step(const void* model_out, int32_t model_out_fp32, int32_t n
 
 /* ---------------------------------------------------------------- sliding-window blend (K10) */
 
-/* All three work on 2-D views (rows x cols, row stride in ELEMENTS) of disparity buffers that are fp32 (a
- * raw pipeline window) or fp64 (an already blended accumulation; the reference's np.ones(float64) result).
+/* All three work on a 3-D region [n0, n1, n2] (frames x rows x cols; strides s0, s1 in ELEMENTS, unit stride
+ * on the last axis) of disparity buffers that are fp32 (a raw pipeline window) or fp64 (an already blended
+ * accumulation; the reference's np.ones(float64) result buffers).
  *
  * aether_scale_reduce: out[0] += sum(f32(p)*f32(t)), out[1] += sum(f32(p)*f32(p)); out is fp64[2], zeroed by
  *   the caller; scale = out[0]/out[1] (0 when out[1] == 0) is compute_scale (postprocess_utils.py:847-864).
- * aether_blend_crossfade: dst = acc * w + (scale*win) * (1-w), w = np.linspace(1,0,n_weights)[k] with
- *   k = column (axis_outer = 0) or row / inner (axis_outer = 1)      (launch_aether.py:217-250, :281-284)
+ * aether_blend_crossfade: dst = acc * w + (scale*win) * (1-w), w = np.linspace(1, 0, n_axis)[index along axis]
+ *   (launch_aether.py:217-250 spatial, axis 2 or 1;  :281-284 temporal, axis 0)
  * aether_scale_copy: dst = apply_scale ? scale*src : src, widened to fp64   (launch_aether.py:220-227, :277-280) */
-int aether_scale_reduce(const void* pred, int32_t pred_is_f64, int64_t pred_rs, const void* target,
-                        int32_t target_is_f64, int64_t target_rs, int64_t rows, int64_t cols, double* out,
-                        void* stream);
-int aether_blend_crossfade(double* dst, int64_t dst_rs, const void* acc, int32_t acc_is_f64, int64_t acc_rs,
-                           const void* win, int32_t win_is_f64, int64_t win_rs, double scale, int64_t rows,
-                           int64_t cols, int64_t inner, int32_t axis_outer, int64_t n_weights, void* stream);
-int aether_scale_copy(double* dst, int64_t dst_rs, const void* src, int32_t src_is_f64, int64_t src_rs, double scale,
-                      int32_t apply_scale, int64_t rows, int64_t cols, void* stream);
+int aether_scale_reduce(const void* pred, int32_t pred_is_f64, int64_t pred_s0, int64_t pred_s1, const void* target,
+                        int32_t target_is_f64, int64_t target_s0, int64_t target_s1, int64_t n0, int64_t n1,
+                        int64_t n2, double* out, void* stream);
+int aether_blend_crossfade(double* dst, int64_t dst_s0, int64_t dst_s1, const void* acc, int32_t acc_is_f64,
+                           int64_t acc_s0, int64_t acc_s1, const void* win, int32_t win_is_f64, int64_t win_s0,
+                           int64_t win_s1, double scale, int64_t n0, int64_t n1, int64_t n2, int32_t axis,
+                           void* stream);
+int aether_scale_copy(double* dst, int64_t dst_s0, int64_t dst_s1, const void* src, int32_t src_is_f64, int64_t src_s0,
+                      int64_t src_s1, double scale, int32_t apply_scale, int64_t n0, int64_t n1, int64_t n2,
+                      void* stream);
 
 #ifdef __cplusplus
 }
