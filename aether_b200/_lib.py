@@ -22,7 +22,8 @@ class DitConfig(C.Structure):
     _fields_ = [("num_heads", c_int32), ("head_dim", c_int32), ("num_layers", c_int32),
                 ("in_channels", c_int32), ("out_channels", c_int32), ("patch_size", c_int32),
                 ("time_embed_dim", c_int32), ("text_embed_dim", c_int32), ("flip_sin_to_cos", c_int32),
-                ("freq_shift", c_float), ("norm_eps", c_float), ("ff_mult", c_int32)]
+                ("freq_shift", c_float), ("norm_eps", c_float), ("ff_mult", c_int32),
+                ("attention_fp16_pv", c_int32)]
 
 
 class DitLayerWeights(C.Structure):
@@ -49,8 +50,9 @@ SIGNATURES = {
     "aether_abi_version": (c_int32, []),
     "aether_device_ok": (c_int32, []),
     "aether_gemm_bf16": (C.c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_int32,
-                                   c_void_p, c_int32, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p]),
-    "aether_attention_bf16": (C.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_float, c_void_p]),
+                                   c_void_p, c_int32, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32,
+                                   c_void_p]),
+    "aether_attention_bf16": (C.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_float, c_int32, c_void_p]),
     "aether_ln_modulate": (C.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p,
                                      c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                      c_void_p]),
@@ -66,6 +68,8 @@ SIGNATURES = {
     "aether_dit_create": (C.c_int, [C.POINTER(DitConfig), C.POINTER(DitWeights), C.POINTER(c_void_p)]),
     "aether_dit_destroy": (None, [c_void_p]),
     "aether_dit_set_pos_embedding": (C.c_int, [c_void_p, c_void_p]),
+    "aether_dit_enable_timing": (C.c_int, [c_void_p, c_int32]),
+    "aether_dit_read_timing": (C.c_int, [c_void_p, C.POINTER(c_float), C.POINTER(c_int32)]),
     "aether_dit_workspace_bytes": (c_int64, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32]),
     "aether_dit_forward": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
                                      c_int32, c_int32, c_int32, c_int32, c_void_p, c_int64, c_int32, c_void_p]),

@@ -4,20 +4,30 @@
 // Replaces F.scaled_dot_product_attention inside diffusers' CogVideoXAttnProcessor2_0, which the
 // reference reaches through aether/pipelines/aetherv1_pipeline_cogvideox.py:865-875 (42 layers x steps).
 // Q and K arrive already QK-LayerNorm'ed and RoPE'd (qk_norm_rope kernel); V is read in place from the
-// fused QKV GEMM output.  All three live in one buffer  qkv[B, S, 3, H, 64]  (bf16) addressed by a single
-// 4-D TMA tensor map {64, 3H, S, B}; O is written token-major  out[B, S, H*64]  so it feeds to_out directly.
+// fused QKV GEMM output.  All three live in one buffer  qkv[B, S, 3, H, 64]  (16-bit elements) addressed
+// by a single 4-D TMA tensor map {64, 3H, S, B}; O is written token-major  out[B, S, H*64]  (bf16) so it
+// feeds to_out directly.
 //
 // CTA = 256 query rows (two 128-row tiles) of one (b, h); 12 warps:
 //   warp 0      TMA producer: Q tiles once, then a 3-stage K ring and a 3-stage V ring (16 KB boxes)
 //   warp 1      MMA issuer  : S_t = Q_t K_j^T   (tcgen05.mma SS, M=128 N=128 K=64 -> 128 fp32 TMEM columns)
-//                             O_t += P_t V_j    (tcgen05.mma TS: A = P_t in TMEM (bf16, aliases S_t),
+//                             O_t += P_t V_j    (tcgen05.mma TS: A = P_t in TMEM (16-bit, aliases S_t),
 //                                                B = V_j shared memory MN-major, M=128 N=64 K=128)
 //               issue order PV_0(j) QK_0(j+1) PV_1(j) QK_1(j+1): the two query tiles ping-pong so the
 //               tensor pipe works on one while the other is in softmax.
 //   warps 4..7  softmax warpgroup for tile 0, warps 8..11 for tile 1: one thread per query row
 //               (tcgen05.ld 32x32b => no shuffles), exp2 with the scale folded in, lazy O rescale
-//               (only when the running max grew by > 2^8), P packed to bf16 and tcgen05.st back.
-// TMEM columns: S0/P0 [0,128) S1/P1 [128,256) O0 [256,320) O1 [320,384)   (512 allocated).
+//               (only when the running max grew by > 2^8), P packed to 16 bit and tcgen05.st back.
+//
+// Two arithmetic modes (template F16PV):
+//   false: P = bf16, V = bf16; exp2 = one fp32 MUFU op per element; row sums on the CUDA cores.
+//   true : P = fp16, V = fp16 (the QKV GEMM epilogue emits the V third as fp16).  The kernel is bound by the
+//          MUFU (16 ex2/clk/SM: 1024 clk per 128x128 tile against 512 clk of tensor work), so this mode
+//          (a) computes two exponentials per MUFU op with ex2.approx.f16x2 -- whose packed output IS the P
+//          operand, no separate convert -- after a packed fma.rn.f32x2 scale/subtract, and (b) moves the row
+//          sums to the tensor core: L_t += P_t * Ones, a 16-column N-tile whose B operand is a constant
+//          2 KB shared-memory tile (row 0 = 1.0), so l is the fp32 sum of exactly the P values used for O.
+// TMEM columns: S0/P0 [0,128) S1/P1 [128,256) O0 [256,320) O1 [320,384) L0 [384,400) L1 [400,416) of 512.
 // Roofline: tensor;  algorithmic flop / launch = 4 * B * H * S^2 * 64.
 #include "host_util.h"
 #include "ptx.cuh"
@@ -30,10 +40,11 @@ constexpr int BQ = 128;          // rows per query tile (2 tiles per CTA)
 constexpr int BKV = 128;         // keys per tile
 constexpr int KSTAGES = 3, VSTAGES = 3;
 constexpr int TILE_BYTES = BQ * DH * 2;   // 16 KB (same for Q, K, V tiles)
-constexpr int SMEM_BYTES = 1024 + (2 + KSTAGES + VSTAGES) * TILE_BYTES + 256;
+constexpr int ONES_BYTES = 2048;          // 16 rows x 128 B, K-major SW128 (row 0 = fp16 ones)
+constexpr int SMEM_BYTES = 1024 + (2 + KSTAGES + VSTAGES) * TILE_BYTES + ONES_BYTES + 256;
 constexpr int THREADS = 384;
 
-constexpr uint32_t COL_S0 = 0, COL_S1 = 128, COL_O0 = 256, COL_O1 = 320;
+constexpr uint32_t COL_S0 = 0, COL_S1 = 128, COL_O0 = 256, COL_O1 = 320, COL_L0 = 384, COL_L1 = 400;
 
 struct Params {
   int B, H, S;
@@ -41,14 +52,17 @@ struct Params {
   float scale_log2;         // dh^-0.5 * log2(e)
 };
 
+template <int MODE>   // 0: bf16 P/V   1: fp16 P/V, MUFU exp   2: fp16 P/V, 40% of the exponentials on the FMA pipe
 __global__ void __launch_bounds__(THREADS, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Params p) {
+  constexpr bool F16PV = MODE != 0;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_q = smem;                               // 2 tiles
   uint8_t* smem_k = smem + 2 * TILE_BYTES;              // KSTAGES tiles
   uint8_t* smem_v = smem_k + KSTAGES * TILE_BYTES;      // VSTAGES tiles
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_v + VSTAGES * TILE_BYTES);
+  uint8_t* smem_ones = smem_v + VSTAGES * TILE_BYTES;   // 2 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_ones + ONES_BYTES);
   uint64_t* q_full = bars;                  // [2]
   uint64_t* k_full = q_full + 2;            // [KSTAGES]
   uint64_t* k_empty = k_full + KSTAGES;     // [KSTAGES]
@@ -84,6 +98,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Params p) {
     }
     fence_mbar_init();
   }
+  if (F16PV && warp == 3) {
+    // constant B operand of the row-sum MMA: 16 (N) x 64 (K) fp16, K-major, row 0 = 1.0, rows 1..15 = 0.
+    // The 128B swizzle only permutes 16-byte chunks inside a row, so a constant row needs no swizzling.
+    uint32_t* o32 = reinterpret_cast<uint32_t*>(smem_ones);
+    for (int i = lane; i < ONES_BYTES / 4; i += 32) o32[i] = (i < 32) ? 0x3C003C00u : 0u;
+    fence_proxy_async_smem();
+  }
   if (warp == 2) tmem_alloc<512>(tmem_base_ptr);
   tc_fence_before();
   __syncthreads();
@@ -112,10 +133,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Params p) {
       }
     } else if (warp == 1 && lane == 0) {
       // ---------------------------------------------------------------- MMA issuer
-      constexpr uint32_t idesc_qk = make_idesc_bf16(BQ, BKV, 0, 0);   // A = Q K-major, B = K K-major
-      constexpr uint32_t idesc_pv = make_idesc_bf16(BQ, DH, 0, 1);    // A = P (TMEM),  B = V MN-major
+      constexpr uint32_t PV_FMT = F16PV ? 0u : 1u;                                      // 0 = F16, 1 = BF16
+      constexpr uint32_t idesc_qk = make_idesc_f16kind(BQ, BKV, 1, 1, 0, 0);            // Q, K bf16, both K-major
+      constexpr uint32_t idesc_pv = make_idesc_f16kind(BQ, DH, PV_FMT, PV_FMT, 0, 1);   // P (TMEM), V MN-major
+      constexpr uint32_t idesc_l = make_idesc_f16kind(BQ, 16, 0, 0, 0, 0);              // P (TMEM), Ones K-major
       const uint32_t s_col[2] = {tmem_base + COL_S0, tmem_base + COL_S1};
       const uint32_t o_col[2] = {tmem_base + COL_O0, tmem_base + COL_O1};
+      const uint32_t l_col[2] = {tmem_base + COL_L0, tmem_base + COL_L1};
+      const uint64_t ones_desc = make_sw128_desc(smem_u32(smem_ones));
       uint64_t q_desc[2];
       for (int t = 0; t < 2; ++t) q_desc[t] = make_sw128_desc(smem_u32(smem_q + t * TILE_BYTES));
 
@@ -127,8 +152,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Params p) {
       auto issue_pv = [&](int t, int vs, bool first) {
         const uint64_t v_desc = make_sw128_desc(smem_u32(smem_v + vs * TILE_BYTES));
 #pragma unroll
-        for (int k = 0; k < BKV / 16; ++k)   // 16 keys per step: P advances 8 TMEM columns, V 16 rows = 2048 B
-          tc_mma_ts(o_col[t], s_col[t] + 8 * k, v_desc + 128 * k, idesc_pv, (!first || k > 0) ? 1u : 0u);
+        for (int k = 0; k < BKV / 16; ++k) {  // 16 keys per step: P advances 8 TMEM columns, V 16 rows = 2048 B
+          const uint32_t acc = (!first || k > 0) ? 1u : 0u;
+          tc_mma_ts(o_col[t], s_col[t] + 8 * k, v_desc + 128 * k, idesc_pv, acc);
+          if (F16PV) tc_mma_ts(l_col[t], s_col[t] + 8 * k, ones_desc, idesc_l, acc);
+        }
       };
 
       int ks = 0, vs = 0;
@@ -187,10 +215,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Params p) {
     const uint32_t lane_off = uint32_t(q * 32) << 16;
     const uint32_t s_addr = tmem_base + lane_off + (t == 0 ? COL_S0 : COL_S1);
     const uint32_t o_addr = tmem_base + lane_off + (t == 0 ? COL_O0 : COL_O1);
+    const uint32_t l_addr = tmem_base + lane_off + (t == 0 ? COL_L0 : COL_L1);
     const float sl2 = p.scale_log2;
     const float rescale_thresh = 8.0f / sl2;       // in raw-score units
     float m_used = -INFINITY;                      // reference max currently baked into O and l
-    float l = 0.f;
+    float l = 0.f;                                 // row sum (F16PV: kept in TMEM by the Ones MMA instead)
     uint32_t sph = 0;
 
     for (int j = 0; j < n_kv; ++j) {
@@ -233,6 +262,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Params p) {
           uint32_t o0[32], o1[32];
           tmem_ld_32x32b_x32(o_addr, o0);
           tmem_ld_32x32b_x32(o_addr + 32, o1);
+          uint32_t lv = 0;
+          if (F16PV) tmem_ld_32x32b_x1(l_addr, lv);
           tc_wait_ld();
 #pragma unroll
           for (int c = 0; c < 32; ++c) {
@@ -241,22 +272,34 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Params p) {
           }
           tmem_st_32x32b_x32(o_addr, o0);
           tmem_st_32x32b_x32(o_addr + 32, o1);
+          if (F16PV) tmem_st_32x32b_x1(l_addr, __float_as_uint(__uint_as_float(lv) * alpha));
         }
       }
       const float neg_m = -m_used * sl2;
-      float sum[8];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) sum[c] = 0.f;
       uint32_t pk[64];
+      if (F16PV) {
+        const uint64_t sl2x2 = pack_f32x2(sl2, sl2), negx2 = pack_f32x2(neg_m, neg_m);
 #pragma unroll
-      for (int c = 0; c < 128; c += 2) {
-        const float p0 = fast_exp2(fmaf(__uint_as_float(s[c]), sl2, neg_m));
-        const float p1 = fast_exp2(fmaf(__uint_as_float(s[c + 1]), sl2, neg_m));
-        sum[c & 7] += p0;
-        sum[(c + 1) & 7] += p1;
-        pk[c >> 1] = pack_bf16x2(p0, p1);
+        for (int c = 0; c < 128; c += 2) {
+          const uint64_t x2 = ffma2(pack_f32x2(__uint_as_float(s[c]), __uint_as_float(s[c + 1])), sl2x2, negx2);
+          // MODE 2: pairs 1 and 3 of every 5 (40 %) bypass the MUFU (FA4-style software exp2)
+          const bool poly = (MODE == 2) && (((c >> 1) % 5 == 1) || ((c >> 1) % 5 == 3));
+          pk[c >> 1] = poly ? exp2_poly_f16x2_from_f32x2(x2) : exp2_f16x2_from_f32x2(x2);
+        }
+      } else {
+        float sum[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) sum[c] = 0.f;
+#pragma unroll
+        for (int c = 0; c < 128; c += 2) {
+          const float p0 = fast_exp2(fmaf(__uint_as_float(s[c]), sl2, neg_m));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(s[c + 1]), sl2, neg_m));
+          sum[c & 7] += p0;
+          sum[(c + 1) & 7] += p1;
+          pk[c >> 1] = pack_bf16x2(p0, p1);
+        }
+        l += ((sum[0] + sum[1]) + (sum[2] + sum[3])) + ((sum[4] + sum[5]) + (sum[6] + sum[7]));
       }
-      l += ((sum[0] + sum[1]) + (sum[2] + sum[3])) + ((sum[4] + sum[5]) + (sum[6] + sum[7]));
       {
         const uint32_t(&p0)[32] = *reinterpret_cast<const uint32_t(*)[32]>(&pk[0]);
         const uint32_t(&p1)[32] = *reinterpret_cast<const uint32_t(*)[32]>(&pk[32]);
@@ -274,7 +317,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Params p) {
     uint32_t o0[32], o1[32];
     tmem_ld_32x32b_x32(o_addr, o0);
     tmem_ld_32x32b_x32(o_addr + 32, o1);
-    tc_wait_ld();
+    if (F16PV) {
+      uint32_t lv;
+      tmem_ld_32x32b_x1(l_addr, lv);
+      tc_wait_ld();
+      l = __uint_as_float(lv);
+    } else {
+      tc_wait_ld();
+    }
     const int row = q0 + t * BQ + row_in_tile;
     if (row < p.S) {
       const float inv = 1.0f / l;
@@ -308,36 +358,48 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Params p) {
   }
 }
 
+template <int MODE>
+static int launch(const CUtensorMap& tm, const Params& p, dim3 grid, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    AETHER_CUDA_OK(cudaFuncSetAttribute(attention_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        SMEM_BYTES));
+    attr_set = true;
+  }
+  attention_kernel<MODE><<<grid, THREADS, SMEM_BYTES, stream>>>(tm, p);
+  AETHER_CUDA_OK(cudaGetLastError());
+  return AETHER_OK;
+}
+
 }  // namespace attn
 
-int attention_bf16(const void* qkv, void* out, int B, int S, int H, float softmax_scale, cudaStream_t stream) {
+// v_fp16 != 0: the V third of qkv holds fp16 values (GEMM f16_from_col) and an fp16-P mode runs:
+//   1 = every exponential on the MUFU, 2 = 40 % of them as an FMA-pipe polynomial (the product default).
+int attention_bf16(const void* qkv, void* out, int B, int S, int H, float softmax_scale, int v_fp16,
+                   cudaStream_t stream) {
   AETHER_CHECK_ARG(B > 0 && S > 0 && H > 0);
   AETHER_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0);
   CUtensorMap tm;
   const uint64_t dims[4] = {64, uint64_t(3 * H), uint64_t(S), uint64_t(B)};
   const uint64_t strides[3] = {128, uint64_t(3 * H) * 128, uint64_t(S) * uint64_t(3 * H) * 128};
   const uint32_t box[4] = {64, 1, uint32_t(attn::BKV), 1};
-  int rc = make_tmap_bf16(&tm, qkv, 4, dims, strides, box, true);
+  int rc = make_tmap_bf16(&tm, qkv, 4, dims, strides, box, true);   // 16-bit elements; the type only sizes the copy
   if (rc) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    AETHER_CUDA_OK(cudaFuncSetAttribute(attn::attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        attn::SMEM_BYTES));
-    attr_set = true;
-  }
   attn::Params p;
   p.B = B; p.H = H; p.S = S;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
   dim3 grid((unsigned)ceil_div(S, 2 * attn::BQ), (unsigned)H, (unsigned)B);
-  attn::attention_kernel<<<grid, attn::THREADS, attn::SMEM_BYTES, stream>>>(tm, p);
-  AETHER_CUDA_OK(cudaGetLastError());
-  return AETHER_OK;
+  switch (v_fp16) {
+    case 0: return attn::launch<0>(tm, p, grid, stream);
+    case 1: return attn::launch<1>(tm, p, grid, stream);
+    default: return attn::launch<2>(tm, p, grid, stream);
+  }
 }
 
 }  // namespace aether
 
 extern "C" int aether_attention_bf16(const void* qkv, void* out, int32_t B, int32_t S, int32_t H,
-                                     float softmax_scale, void* stream) {
-  return aether::attention_bf16(qkv, out, B, S, H, softmax_scale, reinterpret_cast<cudaStream_t>(stream));
+                                     float softmax_scale, int32_t v_fp16, void* stream) {
+  return aether::attention_bf16(qkv, out, B, S, H, softmax_scale, v_fp16, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -16,8 +16,9 @@
 namespace aether {
 int gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int M, int N, int K,
               const float* bias, int epilogue, const float* gate_vid, const float* gate_txt, int64_t gate_bstride,
-              int S, int St, cudaStream_t stream);
-int attention_bf16(const void* qkv, void* out, int B, int S, int H, float softmax_scale, cudaStream_t stream);
+              int S, int St, int f16_from_col, cudaStream_t stream);
+int attention_bf16(const void* qkv, void* out, int B, int S, int H, float softmax_scale, int v_fp16,
+                   cudaStream_t stream);
 int ln_modulate(const void* x, void* y, int B, int S, int St, int D, const float* gamma, const float* beta, float eps,
                 const float* gamma2, const float* beta2, const float* shift_vid, const float* scale_vid,
                 const float* shift_txt, const float* scale_txt, int64_t mod_bstride, cudaStream_t stream);
@@ -35,6 +36,11 @@ struct AetherDit {
   AetherDitConfig cfg;
   AetherDitWeights w;
   AetherDitLayerWeights* layers;
+  // optional live timing of the dominant kernel (attention): one CUDA event pair per layer, recorded on the
+  // launching stream, read back by aether_dit_read_timing after the caller synchronised.
+  bool timing = false;
+  cudaEvent_t* ev = nullptr;     // [2 * num_layers]
+  int ev_used = 0;               // launches recorded by the last forward
 };
 
 namespace {
@@ -102,8 +108,37 @@ extern "C" int aether_dit_create(const AetherDitConfig* cfg, const AetherDitWeig
 
 extern "C" void aether_dit_destroy(AetherDit* h) {
   if (!h) return;
+  if (h->ev) {
+    for (int i = 0; i < 2 * h->cfg.num_layers; ++i) cudaEventDestroy(h->ev[i]);
+    delete[] h->ev;
+  }
   delete[] h->layers;
   delete h;
+}
+
+extern "C" int aether_dit_enable_timing(AetherDit* h, int32_t enable) {
+  if (!h) return AETHER_ERR_INVALID;
+  if (enable && !h->ev) {
+    h->ev = new (std::nothrow) cudaEvent_t[2 * h->cfg.num_layers];
+    if (!h->ev) return AETHER_ERR_INVALID;
+    for (int i = 0; i < 2 * h->cfg.num_layers; ++i) AETHER_CUDA_OK(cudaEventCreate(&h->ev[i]));
+  }
+  h->timing = enable != 0;
+  h->ev_used = 0;
+  return AETHER_OK;
+}
+
+extern "C" int aether_dit_read_timing(AetherDit* h, float* attention_ms_total, int32_t* attention_launches) {
+  if (!h || !attention_ms_total || !attention_launches || !h->ev) return AETHER_ERR_INVALID;
+  float total = 0.f;
+  for (int i = 0; i < h->ev_used; ++i) {
+    float ms = 0.f;
+    AETHER_CUDA_OK(cudaEventElapsedTime(&ms, h->ev[2 * i], h->ev[2 * i + 1]));   // fails if not yet complete
+    total += ms;
+  }
+  *attention_ms_total = total;
+  *attention_launches = h->ev_used;
+  return AETHER_OK;
 }
 
 extern "C" int aether_dit_set_pos_embedding(AetherDit* h, const void* pos_bf16) {
@@ -164,9 +199,9 @@ extern "C" int aether_dit_forward(AetherDit* h, const void* hidden_in, const voi
     if (St > 0)
       RUN(gemm_bf16(reinterpret_cast<const char*>(text) + int64_t(b) * St * c.text_embed_dim * 2, c.text_embed_dim,
                     h->w.w_text, c.text_embed_dim, hb, D, St, D, c.text_embed_dim, h->w.b_text, 0, nullptr, nullptr,
-                    0, 0, 0, stream));
+                    0, 0, 0, -1, stream));
     RUN(gemm_bf16(patches + int64_t(b) * Sv * Kp * 2, Kp, h->w.w_patch, Kp, hb + int64_t(St) * D * 2, D, Sv, D, Kp,
-                  h->w.b_patch, 0, nullptr, nullptr, 0, 0, 0, stream));
+                  h->w.b_patch, 0, nullptr, nullptr, 0, 0, 0, -1, stream));
   }
   if (h->w.pos_embedding) RUN(add_pos_embed(ws.hidden, h->w.pos_embedding, B, S, D, stream));
 
@@ -181,18 +216,23 @@ extern "C" int aether_dit_forward(AetherDit* h, const void* hidden_in, const voi
     RUN(ln_modulate(ws.hidden, ws.xn, B, S, St, D, lw.norm1_g, lw.norm1_b, c.norm_eps, nullptr, nullptr, m1, m1 + D,
                     m1 + 3 * D, m1 + 4 * D, mod_stride, stream));
     RUN(gemm_bf16(ws.xn, D, lw.w_qkv, D, ws.qkv, 3 * D, rows, 3 * D, D, lw.b_qkv, 0, nullptr, nullptr, 0, 0, 0,
-                  stream));
+                  c.attention_fp16_pv ? 2 * D : -1, stream));
     RUN(qk_norm_rope(ws.qkv, B, S, St, c.num_heads, lw.qn_g, lw.qn_b, lw.kn_g, lw.kn_b, 1e-6f, rope_cos, rope_sin,
                      stream));
-    RUN(attention_bf16(ws.qkv, ws.attn, B, S, c.num_heads, softmax_scale, stream));
+    if (h->timing) AETHER_CUDA_OK(cudaEventRecord(h->ev[2 * l], stream));
+    RUN(attention_bf16(ws.qkv, ws.attn, B, S, c.num_heads, softmax_scale, c.attention_fp16_pv, stream));
+    if (h->timing) {
+      AETHER_CUDA_OK(cudaEventRecord(h->ev[2 * l + 1], stream));
+      h->ev_used = l + 1;
+    }
     RUN(gemm_bf16(ws.attn, D, lw.w_out, D, ws.hidden, D, rows, D, D, lw.b_out, 2, m1 + 2 * D, m1 + 5 * D, mod_stride,
-                  S, St, stream));
+                  S, St, -1, stream));
     RUN(ln_modulate(ws.hidden, ws.xn, B, S, St, D, lw.norm2_g, lw.norm2_b, c.norm_eps, nullptr, nullptr, m2, m2 + D,
                     m2 + 3 * D, m2 + 4 * D, mod_stride, stream));
     RUN(gemm_bf16(ws.xn, D, lw.w_ff1, D, ws.ffh, int64_t(c.ff_mult) * D, rows, c.ff_mult * D, D, lw.b_ff1, 1, nullptr,
-                  nullptr, 0, 0, 0, stream));
+                  nullptr, 0, 0, 0, -1, stream));
     RUN(gemm_bf16(ws.ffh, int64_t(c.ff_mult) * D, lw.w_ff2, int64_t(c.ff_mult) * D, ws.hidden, D, rows, D,
-                  c.ff_mult * D, lw.b_ff2, 2, m2 + 2 * D, m2 + 5 * D, mod_stride, S, St, stream));
+                  c.ff_mult * D, lw.b_ff2, 2, m2 + 2 * D, m2 + 5 * D, mod_stride, S, St, -1, stream));
   }
 
   // ---- tail: norm_final -> norm_out (AdaLayerNorm, chunk order shift, scale) -> proj_out -> unpatchify
@@ -202,7 +242,7 @@ extern "C" int aether_dit_forward(AetherDit* h, const void* hidden_in, const voi
   char* proj = ws.ffh;   // [B*Sv, Np]
   for (int b = 0; b < B; ++b)
     RUN(gemm_bf16(ws.xn + (int64_t(b) * S + St) * D * 2, D, h->w.w_proj, D, proj + int64_t(b) * Sv * Np * 2, Np, Sv, Np,
-                  D, h->w.b_proj, 0, nullptr, nullptr, 0, 0, 0, stream));
+                  D, h->w.b_proj, 0, nullptr, nullptr, 0, 0, 0, -1, stream));
   RUN(unpatchify(proj, Np, out, B, F, c.out_channels, H, W, stream));
 #undef RUN
   return AETHER_OK;

@@ -40,6 +40,7 @@ struct Params {
   int S, St;                // row -> (b = row / S, s = row % S)
   __nv_bfloat16* C;         // EPI 2 reads the residual from C (in place)
   int64_t ldc;
+  int f16_from;             // output columns >= f16_from are written as fp16 instead of bf16 (V third of QKV)
 };
 
 __device__ __forceinline__ void tile_coords(int t, const Params& p, int& m_blk, int& n_blk) {
@@ -220,8 +221,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
               x[6] = bf16_lo(r.w) + g1.z * x[6]; x[7] = bf16_hi(r.w) + g1.w * x[7];
             }
           }
+          if (n >= p.f16_from) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) packed[g8 * 4 + j] = pack_bf16x2(x[2 * j], x[2 * j + 1]);
+            for (int j = 0; j < 4; ++j) packed[g8 * 4 + j] = pack_f16x2(x[2 * j], x[2 * j + 1]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) packed[g8 * 4 + j] = pack_bf16x2(x[2 * j], x[2 * j + 1]);
+          }
         }
         // staging buffer `cbuf` was last used two chunks ago; make sure that TMA store has read it
         if (store_leader) tma_store_wait_read<1>();
@@ -276,8 +282,9 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, 
 
 int gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int M, int N, int K,
               const float* bias, int epilogue, const float* gate_vid, const float* gate_txt, int64_t gate_bstride,
-              int S, int St, cudaStream_t stream) {
+              int S, int St, int f16_from_col, cudaStream_t stream) {
   AETHER_CHECK_ARG(M > 0 && N > 0 && K > 0);
+  AETHER_CHECK_ARG(f16_from_col < 0 || f16_from_col % 8 == 0);
   AETHER_CHECK_ARG(N % 8 == 0 && K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldc % 8 == 0);
   AETHER_CHECK_ARG(epilogue >= 0 && epilogue <= 2);
   AETHER_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
@@ -297,6 +304,7 @@ int gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, i
   p.S = S > 0 ? S : M; p.St = St;
   p.C = reinterpret_cast<__nv_bfloat16*>(C);
   p.ldc = ldc;
+  p.f16_from = f16_from_col < 0 ? 0x7fffffff : f16_from_col;
   switch (epilogue) {
     case 0: return gemm::launch<0>(ta, tb, tc, p, stream);
     case 1: return gemm::launch<1>(ta, tb, tc, p, stream);
@@ -309,7 +317,7 @@ int gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, i
 extern "C" int aether_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc,
                                 int32_t M, int32_t N, int32_t K, const float* bias, int32_t epilogue,
                                 const float* gate_vid, const float* gate_txt, int64_t gate_bstride, int32_t S,
-                                int32_t St, void* stream) {
+                                int32_t St, int32_t f16_from_col, void* stream) {
   return aether::gemm_bf16(A, lda, W, ldw, C, ldc, M, N, K, bias, epilogue, gate_vid, gate_txt, gate_bstride, S, St,
-                           reinterpret_cast<cudaStream_t>(stream));
+                           f16_from_col, reinterpret_cast<cudaStream_t>(stream));
 }

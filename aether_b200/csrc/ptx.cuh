@@ -194,6 +194,18 @@ __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_
       : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld_32x32b_x1(uint32_t taddr, uint32_t& r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];\n" : "=r"(r) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x1(uint32_t taddr, uint32_t r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};\n" ::"r"(taddr), "r"(r) : "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);   // .x = lo (low 16 bits), .y = hi
   return *reinterpret_cast<uint32_t*>(&v);
@@ -205,6 +217,64 @@ __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+// kind::f16 instruction descriptor with explicit operand formats (0 = F16, 1 = BF16), D = F32.
+__host__ __device__ constexpr uint32_t make_idesc_f16kind(uint32_t M, uint32_t N, uint32_t a_fmt, uint32_t b_fmt,
+                                                          uint32_t a_mn_major, uint32_t b_mn_major) {
+  return (1u << 4) | (a_fmt << 7) | (b_fmt << 10) | (a_mn_major << 15) | (b_mn_major << 16) | ((N >> 3) << 17) |
+         ((M >> 4) << 24);
+}
+
+// Packed fp32x2 FMA (Blackwell FFMA2): d.{lo,hi} = a.{lo,hi} * b.{lo,hi} + c.{lo,hi}; operands are 64-bit pairs.
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+// exp2 of a packed fp32 pair WITHOUT the MUFU: Cody-Waite range reduction (x = j + f, j = round(x) through the
+// 1.5*2^23 magic-number add, f in [-0.5, 0.5]) and a cubic minimax polynomial for 2^f (max rel. error 7.5e-5,
+// below fp16 rounding), all on the FMA pipe with packed fma/add.f32x2; 2^j is applied by adding j << 23 to
+// the result's exponent field.  x is clamped to >= -126 (covers -inf from masked keys).  Returns f16x2.
+__device__ __forceinline__ uint32_t exp2_poly_f16x2_from_f32x2(uint64_t x) {
+  float x0, x1;
+  unpack_f32x2(x, x0, x1);
+  const uint64_t xc = pack_f32x2(fmaxf(x0, -126.f), fmaxf(x1, -126.f));
+  const uint64_t t = fadd2(xc, pack_f32x2(12582912.f, 12582912.f));
+  const uint64_t jf = fadd2(t, pack_f32x2(-12582912.f, -12582912.f));
+  const uint64_t f = ffma2(jf, pack_f32x2(-1.f, -1.f), xc);
+  uint64_t pl = ffma2(f, pack_f32x2(0.055171460f, 0.055171460f), pack_f32x2(0.24261086f, 0.24261086f));
+  pl = ffma2(pl, f, pack_f32x2(0.69326097f, 0.69326097f));
+  pl = ffma2(pl, f, pack_f32x2(0.99992812f, 0.99992812f));
+  float p0, p1, t0, t1;
+  unpack_f32x2(pl, p0, p1);
+  unpack_f32x2(t, t0, t1);
+  const float r0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(t0) << 23));
+  const float r1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
+  uint32_t h;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(r1), "f"(r0));
+  return h;
+}
+// exp2 of two fp32 values given as a packed pair, computed as ONE half-precision MUFU op:
+// cvt.rn.f16x2.f32 (hi -> upper half, lo -> lower half) then ex2.approx.f16x2.  Result: packed f16x2 (lo in [15:0]).
+__device__ __forceinline__ uint32_t exp2_f16x2_from_f32x2(uint64_t x) {
+  uint32_t h, p;
+  asm("{\n\t.reg .f32 lo, hi;\n\tmov.b64 {lo, hi}, %1;\n\tcvt.rn.f16x2.f32 %0, hi, lo;\n\t}\n" : "=r"(h) : "l"(x));
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(p) : "r"(h));
+  return p;
 }
 
 template <int REGS>

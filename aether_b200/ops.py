@@ -24,8 +24,10 @@ def _need(t: torch.Tensor, dtype, name: str):
 
 
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, epilogue: int = 0,
-         out: Optional[torch.Tensor] = None, gate_vid=None, gate_txt=None, S: int = 0, St: int = 0) -> torch.Tensor:
-    """out[M,N] = epi(a[M,K] @ w[N,K]^T).  epilogue 2 updates `out` in place (out = out + gate * (acc + bias))."""
+         out: Optional[torch.Tensor] = None, gate_vid=None, gate_txt=None, S: int = 0, St: int = 0,
+         f16_from_col: int = -1) -> torch.Tensor:
+    """out[M,N] = epi(a[M,K] @ w[N,K]^T).  epilogue 2 updates `out` in place (out = out + gate * (acc + bias)).
+    Columns >= f16_from_col of the (bf16-typed) output hold fp16 bit patterns."""
     lib = _lib.require_device()
     _need(a, BF16, "a"); _need(w, BF16, "w")
     M, K = a.shape
@@ -40,19 +42,21 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     if bias is not None:
         _need(bias, F32, "bias")
     check(lib.aether_gemm_bf16(ptr(a), a.stride(0), ptr(w), w.stride(0), ptr(out), out.stride(0), M, N, K, ptr(bias),
-                               epilogue, ptr(gate_vid), ptr(gate_txt), gb, S, St, current_stream()), "gemm_bf16")
+                               epilogue, ptr(gate_vid), ptr(gate_txt), gb, S, St, f16_from_col, current_stream()),
+          "gemm_bf16")
     return out
 
 
-def attention(qkv: torch.Tensor, scale: Optional[float] = None) -> torch.Tensor:
-    """qkv [B,S,3,H,64] bf16 -> out [B,S,H*64] bf16."""
+def attention(qkv: torch.Tensor, scale: Optional[float] = None, v_fp16: bool = False) -> torch.Tensor:
+    """qkv [B,S,3,H,64] bf16 -> out [B,S,H*64] bf16.  With v_fp16 the V third holds fp16 bit patterns
+    (`qkv.view(torch.float16)[:, :, 2] = v.half()`) and the fp16-PV kernel mode runs."""
     lib = _lib.require_device()
     _need(qkv, BF16, "qkv")
     B, S, three, H, dh = qkv.shape
     assert three == 3 and dh == 64
     out = torch.empty(B, S, H * dh, dtype=BF16, device=qkv.device)
     check(lib.aether_attention_bf16(ptr(qkv), ptr(out), B, S, H, float(scale if scale is not None else dh ** -0.5),
-                                    current_stream()), "attention_bf16")
+                                    int(v_fp16), current_stream()), "attention_bf16")
     return out
 
 

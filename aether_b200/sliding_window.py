@@ -115,9 +115,9 @@ def gather_tiles(local: Sequence[Tuple[int, torch.Tensor]], n_tiles: int, rank: 
     for j, (k, d) in enumerate(local):
         assert k == rank + j * world_size
         send[j].copy_(d)
-    recv = torch.empty((world_size,) + tuple(send.shape), dtype=ref.dtype, device=ref.device)
-    dist.all_gather_into_tensor(recv, send, group=group)
-    return [recv[k % world_size, k // world_size] for k in range(n_tiles)]
+    recv = torch.empty((world_size * n_max,) + tuple(ref.shape), dtype=ref.dtype, device=ref.device)
+    dist.all_gather_into_tensor(recv, send, group=group)      # rank r's block lands at rows [r*n_max, (r+1)*n_max)
+    return [recv[(k % world_size) * n_max + k // world_size] for k in range(n_tiles)]
 
 
 # ------------------------------------------------------------------------------------------ K10 wrappers

@@ -128,6 +128,9 @@ class AetherTransformer3D(nn.Module):
         self._packed = None
         self._ws = None
         self._n_layers_override = -1
+        # kernel-mode switch (not a model hyper-parameter): fp16 P/V attention with ex2.f16x2 (default) or the
+        # bf16 P/V variant; set before pack().
+        self.attention_fp16_pv = 2     # 0: bf16 P/V, 1: fp16 P/V (MUFU exp), 2: fp16 P/V + 40% polynomial exp
 
     # ------------------------------------------------------------------ torch plumbing
     @property
@@ -264,7 +267,7 @@ class AetherTransformer3D(nn.Module):
         w.layers = C.cast(layers, C.POINTER(DitLayerWeights))
         cfg = DitConfig(c.num_attention_heads, c.attention_head_dim, c.num_layers, c.in_channels, c.out_channels,
                         c.patch_size, c.time_embed_dim, c.text_embed_dim, int(c.flip_sin_to_cos), float(c.freq_shift),
-                        float(c.norm_eps), c.ff_mult)
+                        float(c.norm_eps), c.ff_mult, int(self.attention_fp16_pv))
         h = C.c_void_p()
         check(lib.aether_dit_create(C.byref(cfg), C.byref(w), C.byref(h)), "dit_create")
         self._handle = h
@@ -293,6 +296,22 @@ class AetherTransformer3D(nn.Module):
                                   c.temporal_interpolation_scale).to(self.device)
         cache[key] = pos.to(torch.bfloat16).contiguous()
         return cache[key]
+
+    # ------------------------------------------------------------------ measurement hooks (bench.py)
+    def enable_timing(self, enable: bool = True):
+        if self._handle is None:
+            self.pack()
+        check(_lib.load().aether_dit_enable_timing(self._handle, int(enable)), "dit_enable_timing")
+
+    def read_attention_timing(self):
+        """(total ms, launches) of the attention kernel in the last forward; call after a stream synchronize."""
+        ms, n = C.c_float(0), C.c_int32(0)
+        check(_lib.load().aether_dit_read_timing(self._handle, C.byref(ms), C.byref(n)), "dit_read_timing")
+        return ms.value, n.value
+
+    def launches_per_forward(self, batch: int) -> int:
+        """Kernels of this library launched by one forward (see csrc/dit_forward.cu)."""
+        return 4 + 1 + 2 * batch + 8 * self.config.num_layers + 1 + batch + 1
 
     # ------------------------------------------------------------------ forward = one C-ABI call
     @torch.no_grad()

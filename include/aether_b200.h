@@ -46,15 +46,19 @@ int32_t aether_device_ok(void);
  *   epilogue 0: + bias        1: gelu_tanh(+ bias)       2: C = C + gate[b, n] * (acc + bias)   (in place)
  * For epilogue 2 row r belongs to batch b = r / S, token s = r % S; tokens s < St use gate_txt, others
  * gate_vid (both fp32 [B, N] with batch stride gate_bstride elements).
+ * Output columns >= f16_from_col (a multiple of 8; < 0 = none) are written as fp16 instead of bf16 (used for
+ * the V third of the fused QKV projection when the fp16-PV attention mode is on).
  * Replaces nn.Linear inside CogVideoXBlock / CogVideoXPatchEmbed / proj_out (pipeline :865). */
 int aether_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int32_t M,
                      int32_t N, int32_t K, const float* bias, int32_t epilogue, const float* gate_vid,
-                     const float* gate_txt, int64_t gate_bstride, int32_t S, int32_t St, void* stream);
+                     const float* gate_txt, int64_t gate_bstride, int32_t S, int32_t St, int32_t f16_from_col,
+                     void* stream);
 
-/* out[B,S,H*64] = softmax(Q K^T * softmax_scale) V over qkv[B,S,3,H,64] (bf16), non-causal, head_dim 64.
- * Replaces F.scaled_dot_product_attention in CogVideoXAttnProcessor2_0 (pipeline :865). */
+/* out[B,S,H*64] (bf16) = softmax(Q K^T * softmax_scale) V over qkv[B,S,3,H,64], non-causal, head_dim 64.
+ * Q, K are bf16; V is bf16 (v_fp16 = 0) or fp16 (v_fp16 = 1, selects the fp16-P / ex2.f16x2 / tensor-core
+ * row-sum mode).  Replaces F.scaled_dot_product_attention in CogVideoXAttnProcessor2_0 (pipeline :865). */
 int aether_attention_bf16(const void* qkv, void* out, int32_t B, int32_t S, int32_t H, float softmax_scale,
-                          void* stream);
+                          int32_t v_fp16, void* stream);
 
 /* ---------------------------------------------------------------- bandwidth-bound DiT kernels */
 
@@ -100,6 +104,7 @@ typedef struct AetherDitConfig {
   int32_t flip_sin_to_cos;
   float freq_shift, norm_eps;
   int32_t ff_mult;
+  int32_t attention_fp16_pv;   /* 1: fp16 P/V + f16x2 exp attention mode (V emitted as fp16 by the QKV GEMM) */
 } AetherDitConfig;
 
 typedef struct AetherDitLayerWeights {
@@ -134,6 +139,11 @@ void aether_dit_destroy(AetherDit* h);
 /* attach / detach (NULL) the additive positional table bf16 [St+Sv, D] used by the next forwards
  * (CogVideoXPatchEmbed learned / sin-cos branch); the buffer stays owned by the caller. */
 int aether_dit_set_pos_embedding(AetherDit* h, const void* pos_bf16);
+/* Measurement hooks (bench.py roofline): when enabled every attention launch of a forward is bracketed by a
+ * CUDA event pair recorded on the launching stream; after the caller synchronised that stream,
+ * aether_dit_read_timing returns the summed duration and the number of launches of the LAST forward. */
+int aether_dit_enable_timing(AetherDit* h, int32_t enable);
+int aether_dit_read_timing(AetherDit* h, float* attention_ms_total, int32_t* attention_launches);
 /* bytes of scratch the forward needs for batch B, F latent frames of HxW (latent pixels), St text tokens */
 int64_t aether_dit_workspace_bytes(const AetherDit* h, int32_t B, int32_t F, int32_t H, int32_t W, int32_t St);
 /* hidden [B,F,Cin,H,W] bf16; text [B,St,text_dim] bf16; timesteps int64 [B]; cos/sin fp32 [F*(H/p)*(W/p), hd]

@@ -1,0 +1,78 @@
+"""Shared builders for tests and for tests/golden/make_golden.py (test infrastructure; may import oracle/)."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+# tiny geometry used by every pipeline-level parity case: 17 frames of 96x160 -> 5 latent frames of 12x20
+TINY = dict(height=96, width=160, num_frames=17, text_len=18, text_dim=128)
+
+
+def tiny_oracle_modules(dtype=torch.bfloat16, seed=0):
+    """(transformer, vae, scheduler) oracle modules for the tiny geometry, seeded."""
+    from oracle.dit import OracleDiT, seeded_init_, tiny_config
+    from oracle.scheduler import OracleDPMScheduler
+    from oracle.vae import OracleVAE, seeded_vae_init_, tiny_vae_config
+    dit = seeded_init_(OracleDiT(tiny_config()), seed=seed).eval()
+    vae = seeded_vae_init_(OracleVAE(tiny_vae_config()), seed=seed + 1).eval()
+    with torch.no_grad():                      # every implementation sees the same bf16-representable weights
+        for m in (dit, vae):
+            for p in m.parameters():
+                p.copy_(p.bfloat16().float())
+    vae.enable_slicing()
+    vae.enable_tiling()
+    return dit.to(dtype), vae.to(dtype), OracleDPMScheduler()
+
+
+def empty_prompt_embeds(seed=7):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(1, TINY["text_len"], TINY["text_dim"], generator=g) * 0.2).bfloat16()
+
+
+def synthetic_video(num_frames=17, height=96, width=160, seed=3) -> np.ndarray:
+    """float32 [F, H, W, 3] in [0, 1], smooth in space and time."""
+    g = np.random.default_rng(seed)
+    t = np.linspace(0, 1, num_frames)[:, None, None, None]
+    y = np.linspace(0, 1, height)[None, :, None, None]
+    x = np.linspace(0, 1, width)[None, None, :, None]
+    ph = g.uniform(0, 6.28, size=(1, 1, 1, 3))
+    v = 0.5 + 0.25 * np.sin(6.28 * (x * 2 + t) + ph) + 0.2 * np.cos(6.28 * (y * 3 - t * 0.5) + ph * 2)
+    v = v + 0.03 * g.standard_normal(v.shape)
+    return np.clip(v, 0, 1).astype(np.float32)
+
+
+def synthetic_raymap(num_frames=17, h=12, w=20, seed=5) -> np.ndarray:
+    g = np.random.default_rng(seed)
+    base = g.standard_normal((1, 6, h, w)).astype(np.float32)
+    drift = np.linspace(0, 1, num_frames, dtype=np.float32)[:, None, None, None]
+    return (base + drift * g.standard_normal((1, 6, 1, 1)).astype(np.float32)).astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------------------------
+# deterministic stand-in for one pipeline call of the sliding-window path: (tile ranges, crop) -> outputs.
+# Disparity gets a tile-dependent gain so that the masked-LSQ scale alignment has real work to do.
+# ------------------------------------------------------------------------------------------------------
+def fake_tile_outputs(crop: np.ndarray, t_start: int, h_start: int, w_start: int):
+    """crop float64/float32 [F, h, w, 3] -> (rgb float32 [F,h,w,3], disparity float32 [F,h,w])."""
+    crop = np.asarray(crop, dtype=np.float64)
+    gain = 1.0 + 0.07 * ((t_start // 8) % 5) + 0.11 * (1 if w_start > 0 else 0) + 0.13 * (1 if h_start > 0 else 0)
+    disp = (0.2 + crop.mean(axis=-1)) * gain
+    f = np.arange(crop.shape[0], dtype=np.float64)[:, None, None]
+    disp = disp * (1.0 + 0.01 * np.sin(0.37 * (f + t_start)))
+    return crop.astype(np.float32), disp.astype(np.float32)
+
+
+def synthetic_long_clip(t, h, w, seed=11) -> np.ndarray:
+    """float64 [1, t, h, w, 3] like launch_aether.prepare_input (cv2.resize(...)/255.0 -> float64)."""
+    g = np.random.default_rng(seed)
+    yy = np.linspace(0, 1, h)[None, :, None, None]
+    xx = np.linspace(0, 1, w)[None, None, :, None]
+    tt = np.linspace(0, 1, t)[:, None, None, None]
+    ph = g.uniform(0, 6.28, size=(1, 1, 1, 3))
+    v = 0.5 + 0.3 * np.sin(6.28 * (xx * 1.5 + tt * 2) + ph) * np.cos(6.28 * (yy * 2 + tt) + ph)
+    return np.clip(v, 0, 1)[None].astype(np.float64)
+
+
+def subsample(a: np.ndarray, steps) -> np.ndarray:
+    sl = tuple(slice(None, None, s) for s in steps)
+    return np.ascontiguousarray(a[sl])

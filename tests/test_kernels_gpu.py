@@ -76,30 +76,67 @@ def test_gemm_gated_residual():
 
 
 # --------------------------------------------------------------------------------------------- attention
+def _attention_case(qkv_f32, v_fp16):
+    """Run the kernel in either mode; the reference uses exactly the 16-bit-rounded operands the kernel sees."""
+    ops = _ops()
+    qkv = qkv_f32.bfloat16()
+    v_ref = qkv[:, :, 2].float()
+    if v_fp16:
+        vh = qkv_f32[:, :, 2].half()
+        qkv.view(torch.float16)[:, :, 2] = vh          # V third carries fp16 bit patterns
+        v_ref = vh.float()
+    out = ops.attention(qkv, v_fp16=v_fp16)
+    B, S, _, H, _ = qkv.shape
+    q, k = (qkv[:, :, i].float().transpose(1, 2) for i in range(2))
+    ref = torch.nn.functional.scaled_dot_product_attention(q, k, v_ref.transpose(1, 2))
+    return out, ref.transpose(1, 2).reshape(B, S, H * 64)
+
+
+@pytest.mark.parametrize("v_fp16", [0, 1, 2])
 @pytest.mark.parametrize("B,S,H", [(1, 256, 2), (1, 128, 1), (2, 318, 4), (1, 1000, 2), (1, 4276, 4)])
-def test_attention(B, S, H):
-    ops = _ops()
+def test_attention(B, S, H, v_fp16):
     g = torch.Generator(device=DEV).manual_seed(S + H)
-    qkv = torch.randn(B, S, 3, H, 64, device=DEV, generator=g).bfloat16()
-    out = ops.attention(qkv)
-    q, k, v = (qkv[:, :, i].float().transpose(1, 2) for i in range(3))
-    ref = torch.nn.functional.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, S, H * 64)
-    _close(out, ref, 2 ** -6, 1e-2, f"attention B{B} S{S} H{H}")
+    qkv = torch.randn(B, S, 3, H, 64, device=DEV, generator=g)
+    out, ref = _attention_case(qkv, v_fp16)
+    _close(out, ref, 2 ** -6, 1e-2, f"attention B{B} S{S} H{H} fp16={v_fp16}")
 
 
-def test_attention_large_logits():
-    """Rows whose running max grows by more than 2^8 between key tiles exercise the lazy O rescale."""
-    ops = _ops()
+@pytest.mark.parametrize("v_fp16", [0, 1, 2])
+def test_attention_large_logits(v_fp16):
+    """Rows whose running max grows by more than 2^8 between key tiles exercise the lazy O (and l) rescale."""
     g = torch.Generator(device=DEV).manual_seed(11)
     B, S, H = 1, 640, 2
     qkv = torch.randn(B, S, 3, H, 64, device=DEV, generator=g)
     qkv[:, :, 0] *= 4.0
     qkv[:, 300:, 1] *= 6.0          # later keys produce much larger logits
-    qkv = qkv.bfloat16()
-    out = ops.attention(qkv)
-    q, k, v = (qkv[:, :, i].float().transpose(1, 2) for i in range(3))
-    ref = torch.nn.functional.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, S, H * 64)
-    _close(out, ref, 2 ** -6, 2e-2, "attention large logits")
+    out, ref = _attention_case(qkv, v_fp16)
+    _close(out, ref, 2 ** -6, 2e-2, f"attention large logits fp16={v_fp16}")
+
+
+@pytest.mark.parametrize("v_fp16", [0, 1, 2])
+def test_attention_peaked_and_flat_rows(v_fp16):
+    """Nearly one-hot rows (large scale) and nearly uniform rows (tiny scale) in the same launch."""
+    g = torch.Generator(device=DEV).manual_seed(12)
+    B, S, H = 1, 900, 2
+    qkv = torch.randn(B, S, 3, H, 64, device=DEV, generator=g)
+    qkv[:, :450, 0] *= 8.0
+    qkv[:, 450:, 0] *= 0.01
+    out, ref = _attention_case(qkv, v_fp16)
+    _close(out, ref, 2 ** -6, 2e-2, f"attention peaked/flat fp16={v_fp16}")
+
+
+def test_gemm_fp16_columns():
+    """Columns >= f16_from_col are emitted as fp16 (V third of the fused QKV projection)."""
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(21)
+    M, N, K, split = 300, 768, 256, 512
+    a = torch.randn(M, K, device=DEV, generator=g).bfloat16()
+    w = (torch.randn(N, K, device=DEV, generator=g) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device=DEV, generator=g)
+    out = ops.gemm(a, w, bias, 0, f16_from_col=split)
+    ref = a.float() @ w.float().t() + bias
+    _close(out[:, :split], ref[:, :split], 2 ** -7, 2e-2, "bf16 part")
+    _close(out.view(torch.float16)[:, split:], ref[:, split:], 2 ** -10, 2e-3, "fp16 part")
 
 
 # --------------------------------------------------------------------------------------------- HBM kernels

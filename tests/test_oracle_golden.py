@@ -1,0 +1,181 @@
+"""CPU: the oracle restatements and the host-side mirrors against the golden vectors produced by the
+reference's own code (tests/golden/make_golden.py).  Bit-exact where the arithmetic is the same expression
+graph (RoPE table, tile plan, compute_scale, pipeline glue with identical modules/RNG); the blend chain is
+compared at fp64 round-off (identical operations, numpy in both cases)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import (TINY, empty_prompt_embeds, fake_tile_outputs, subsample, synthetic_long_clip, synthetic_raymap,
+                     synthetic_video, tiny_oracle_modules)
+
+
+# ------------------------------------------------------------------------------------------------ RoPE
+@pytest.mark.parametrize("impl", ["oracle", "product"])
+def test_rope_tables_match_reference(golden_dir, impl):
+    g = np.load(golden_dir / "rope.npz")
+    names = sorted({k.split("__")[0] for k in g.files})
+    assert len(names) == 5
+    for name in names:
+        sh, sw, f, fps, gh, gw, step, n = g[f"{name}__meta"].tolist()
+        if impl == "oracle":
+            from oracle.rope import prepare_rotary_positional_embeddings as prep
+            cos, sin = prep(sh * 8, sw * 8, f, sample_height=sh, sample_width=sw, fps=fps)
+        else:
+            from aether_b200.rope import prepare_rotary_positional_embeddings as prep
+            cos, sin = prep(sh * 8, sw * 8, f, patch_size=2, vae_scale_factor_spatial=8, sample_height=sh,
+                            sample_width=sw, attention_head_dim=64, base_fps=12, fps=fps)
+        assert cos.shape == (n, 64) and cos.dtype == torch.float32
+        assert np.array_equal(cos.numpy()[::step], g[f"{name}__cos"]), name
+        assert np.array_equal(sin.numpy()[::step], g[f"{name}__sin"]), name
+        sums = g[f"{name}__sums"]
+        assert cos.double().sum().item() == pytest.approx(sums[0], rel=1e-12)
+        assert sin.double().sum().item() == pytest.approx(sums[1], rel=1e-12, abs=1e-9)
+
+
+def test_rope_preserves_norm():
+    """KAT: a rotation never changes the pairwise norm."""
+    from oracle.rope import apply_rotary_emb, prepare_rotary_positional_embeddings
+    cos, sin = prepare_rotary_positional_embeddings(96, 160, 5, sample_height=12, sample_width=20, fps=8)
+    x = torch.randn(1, 2, cos.shape[0], 64)
+    y = apply_rotary_emb(x, cos, sin)
+    n0 = x.reshape(1, 2, -1, 32, 2).pow(2).sum(-1)
+    n1 = y.reshape(1, 2, -1, 32, 2).pow(2).sum(-1)
+    assert torch.allclose(n0, n1, rtol=1e-5, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ scheduler
+def test_scheduler_known_answers():
+    from oracle.scheduler import OracleDPMScheduler
+    from aether_b200.scheduler import AetherDPMScheduler
+    o, p = OracleDPMScheduler(), AetherDPMScheduler()
+    for n in (50, 4, 2):
+        o.set_timesteps(n)
+        p.set_timesteps(n)
+        assert torch.equal(o.timesteps, p.timesteps.cpu())
+        ts = o.timesteps.tolist()
+        assert ts[0] == 999 and ts[-1] == 1000 // n - 1
+        for i, t in enumerate(ts):
+            tb = ts[i - 1] if i > 0 else None
+            co, cp = o.coefficients(t, tb), p.coefficients(t, tb)
+            for k in ("sqrt_a", "sqrt_1ma", "m1", "m2", "m_noise"):
+                assert float(co[k]) == pytest.approx(cp[k], rel=1e-12, abs=1e-15), (n, t, k)
+            if tb is not None and co["prev_t"] >= 0:
+                assert float(co["m3"]) == pytest.approx(cp["m3"], rel=1e-12)
+                assert float(co["m4"]) == pytest.approx(cp["m4"], rel=1e-12, abs=1e-15)
+        first = o.coefficients(ts[0], None)
+        assert float(first["sqrt_a"]) == 0.0 and float(first["m1"]) == 0.0          # zero terminal SNR: alpha_T = 0
+        last = o.coefficients(ts[-1], ts[-2])
+        assert float(last["m1"]) == 0.0 and float(last["m2"]) == -1.0 and float(last["m_noise"]) == 0.0
+    # last step returns x0 exactly
+    o.set_timesteps(4)
+    x = torch.randn(1, 2, 3, 4).bfloat16()
+    v = torch.randn(1, 2, 3, 4)
+    prev, x0 = o.step(v, torch.randn(1, 2, 3, 4), 249, 499, x)
+    assert torch.equal(prev, x0)
+    assert o.alphas_cumprod[999].item() == 0.0 and o.alphas_cumprod.dtype == torch.float64
+
+
+# ------------------------------------------------------------------------------------------------ blend
+def test_compute_scale_matches_reference(golden_dir):
+    from oracle.blend import compute_scale
+    g = np.load(golden_dir / "compute_scale.npz")
+    for i in range(4):
+        pred, tgt = g[f"c{i}__pred"], g[f"c{i}__target"]
+        assert compute_scale(pred, tgt, np.ones_like(tgt)) == float(g[f"c{i}__scale"])
+    assert float(g["c3__scale"]) == 0.0           # zero denominator -> 0 (postprocess_utils.py:858-862)
+
+
+@pytest.mark.parametrize("name", ["temporal", "horizontal", "vertical"])
+def test_tile_plan_and_blend_match_reference(golden_dir, name):
+    from aether_b200.sliding_window import plan_windows
+    from oracle.blend import blend_all
+    g = np.load(golden_dir / f"sliding_{name}.npz")
+    t, h, w = g["thw"].tolist()
+    plan = plan_windows(t, h, w, t)
+    tiles = np.array([[tl.t_start, tl.t_end, tl.h_start, tl.h_end, tl.w_start, tl.w_end] for tl in plan.tiles])
+    assert np.array_equal(tiles, g["tiles"])
+    obs = synthetic_long_clip(t, h, w)
+    disps = []
+    for tl in plan.tiles:
+        crop = obs[0, tl.t_start:tl.t_end, tl.h_start:tl.h_end, tl.w_start:tl.w_end]
+        disps.append(fake_tile_outputs(crop, tl.t_start, tl.h_start, tl.w_start)[1])
+    final = blend_all(disps, tiles, plan.n_spatial, plan.is_horizontal)
+    assert final.dtype == np.float64 and list(final.shape) == g["disparity_shape"].tolist()
+    np.testing.assert_allclose(subsample(final, (3, 16, 16)), g["disparity_sub"], rtol=1e-12, atol=0)
+    assert final.sum() == pytest.approx(float(g["disparity_sum"]), rel=1e-12)
+
+
+def test_plan_config5_geometry():
+    """512 frames of 480x853 -> 60 temporal x 2 spatial = 120 tiles, overlap 587 px."""
+    from aether_b200.sliding_window import partition_tiles, plan_windows
+    plan = plan_windows(512, 480, 853)
+    assert plan.n_temporal == 60 and plan.n_spatial == 2 and len(plan.tiles) == 120 and plan.is_horizontal
+    assert plan.tiles[0].w_end - plan.tiles[1].w_start == 587
+    assert plan.tiles[-1].t_start == 471 and plan.tiles[-1].t_end == 512
+    parts = [partition_tiles(120, r, 8) for r in range(8)]
+    assert sorted(sum(parts, [])) == list(range(120)) and all(len(p) == 15 for p in parts)
+    # the 9-frame fallback of launch_aether.py:87-89 shrinks the window (and the pipeline then rejects it)
+    assert plan_windows(9, 480, 720).frames_per_window == 9
+
+
+# ------------------------------------------------------------------------------------------------ pipeline glue
+def _product_pipeline_with_oracle_modules():
+    from aether_b200.pipeline import AetherV1PipelineCogVideoX
+    dit, vae, sched = tiny_oracle_modules(torch.bfloat16)
+    return AetherV1PipelineCogVideoX(vae=vae, scheduler=sched, transformer=dit,
+                                     empty_prompt_embeds=empty_prompt_embeds())
+
+
+@pytest.mark.parametrize("name,kw", [
+    ("reconstruction", dict(task="reconstruction", num_inference_steps=3)),
+    ("prediction", dict(task="prediction", num_inference_steps=3)),
+    ("planning", dict(task="planning", num_inference_steps=2, guidance_scale=2.5)),
+    ("reconstruction_fps8", dict(task="reconstruction", num_inference_steps=2, fps=8)),
+])
+def test_pipeline_glue_is_bit_identical_to_reference(golden_dir, name, kw):
+    """aether_b200.pipeline (host mirror) driving the SAME oracle modules with the SAME CPU generator must
+    reproduce the reference pipeline's outputs bit for bit: this pins input preprocessing, latent assembly,
+    raymap fold/unfold, RoPE, dynamic CFG, the loop and the output post-processing to the reference."""
+    g = np.load(golden_dir / f"pipeline_{name}.npz")
+    H, W, F = TINY["height"], TINY["width"], TINY["num_frames"]
+    video = synthetic_video(F, H, W)
+    kw = dict(kw)
+    if kw["task"] == "reconstruction":
+        kw["video"] = video
+    else:
+        kw["image"] = video[0]
+        if kw["task"] == "planning":
+            kw["goal"] = video[-1]
+        else:
+            kw["raymap"] = synthetic_raymap(F, H // 8, W // 8)
+    pipe = _product_pipeline_with_oracle_modules()
+    out = pipe(height=H, width=W, num_frames=F, generator=torch.Generator().manual_seed(42), **kw)
+    assert np.array_equal(out.disparity, g["disparity"])
+    assert np.array_equal(out.raymap, g["raymap"])
+    assert np.array_equal(subsample(out.rgb, (2, 2, 2, 1)), g["rgb_sub"])
+    assert out.rgb.dtype == np.float32 and out.disparity.dtype == np.float32 and out.raymap.dtype == np.float32
+
+
+def test_pipeline_error_messages_match_reference(golden_dir):
+    g = np.load(golden_dir / "pipeline_errors.npz")
+    H, W, F = TINY["height"], TINY["width"], TINY["num_frames"]
+    video = synthetic_video(F, H, W)
+    raymap = synthetic_raymap(F, H // 8, W // 8)
+    pipe = _product_pipeline_with_oracle_modules()
+    bad = {
+        "frames": dict(task="reconstruction", video=video[:9], num_frames=9),
+        "fps": dict(task="reconstruction", video=video, num_frames=F, fps=13),
+        "both": dict(task="prediction", image=video[0], video=video, num_frames=F),
+        "none": dict(task="prediction", num_frames=F),
+        "goal_task": dict(task="prediction", image=video[0], goal=video[1], num_frames=F),
+        "raymap_shape": dict(task="prediction", image=video[0], raymap=raymap[:5], num_frames=F),
+        "task": dict(task="segmentation", video=video, num_frames=F),
+        "hw": dict(task="reconstruction", video=video, num_frames=F, height=100),
+    }
+    for k, kw in bad.items():
+        kw.setdefault("height", H)
+        kw.setdefault("width", W)
+        with pytest.raises(ValueError) as ei:
+            pipe(**kw)
+        assert str(ei.value) == str(g[k]), k

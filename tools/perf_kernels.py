@@ -75,15 +75,18 @@ def main():
     # ------------------------------------------------------------------ attention
     for B in ([1] if quick else [1, 2]):
         qkv = torch.randn(B, S, 3, H, 64, device=DEV, generator=g).bfloat16()
-        med, best = timeit(lambda: ops.attention(qkv), iters=3)
         flops = 4.0 * B * H * S * S * 64
         q, k, v = (qkv[:, :, i].transpose(1, 2) for i in range(3))
         sd_med, _ = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(q, k, v), iters=3)
-        r = dict(B=B, S=S, H=H, ms=med, ms_best=best, tflops=flops / med / 1e9,
-                 frac_of_measured_peak=flops / med / 1e9 / TF_PEAK, torch_sdpa_ms=sd_med,
-                 torch_sdpa_tflops=flops / sd_med / 1e9)
-        print(r, flush=True)
-        res["attention"].append(r)
+        for mode in (0, 1, 2):
+            if mode == 1:     # V third re-encoded as fp16 for the fp16-PV modes
+                qkv.view(torch.float16)[:, :, 2] = qkv[:, :, 2].float().half()
+            med, best = timeit(lambda: ops.attention(qkv, v_fp16=mode), iters=3)
+            r = dict(B=B, S=S, H=H, mode=mode, ms=med, ms_best=best, tflops=flops / med / 1e9,
+                     frac_of_measured_peak=flops / med / 1e9 / TF_PEAK, torch_sdpa_ms=sd_med,
+                     torch_sdpa_tflops=flops / sd_med / 1e9)
+            print(r, flush=True)
+            res["attention"].append(r)
         del qkv
     # ------------------------------------------------------------------ HBM kernels
     x = torch.randn(1, S, D, device=DEV, generator=g).bfloat16()
