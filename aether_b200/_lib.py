@@ -73,6 +73,21 @@ SIGNATURES = {
     "aether_dit_workspace_bytes": (c_int64, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32]),
     "aether_dit_forward": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
                                      c_int32, c_int32, c_int32, c_int32, c_void_p, c_int64, c_int32, c_void_p]),
+    "aether_conv3d_bf16": (C.c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                     c_int32, c_int32, c_void_p]),
+    "aether_gn_workspace_floats": (c_int64, [c_int32]),
+    "aether_gn_stats": (C.c_int, [c_void_p, c_int64, c_int32, c_int32, c_float, c_void_p, c_void_p, c_void_p]),
+    "aether_gn_apply": (C.c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "aether_upsample_nearest": (C.c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                          c_int32, c_int32, c_int32, c_void_p]),
+    "aether_avgpool_time": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_void_p]),
+    "aether_ncthw_to_thwc": (C.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int64, c_void_p]),
+    "aether_thwc_to_ncthw": (C.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int64, c_void_p]),
+    "aether_posterior_sample": (C.c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_int64, c_void_p]),
+    "aether_tile_blend": (C.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                    c_int32, c_void_p]),
     "aether_cfg_dpm_step": (C.c_int, [c_void_p, c_int32, c_int32, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
                                       C.POINTER(DpmCoeffs), c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "aether_scale_reduce": (C.c_int, [c_void_p, c_int32, c_int64, c_int64, c_void_p, c_int32, c_int64, c_int64,

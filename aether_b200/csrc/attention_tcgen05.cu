@@ -55,7 +55,7 @@ struct Params {
 template <int MODE>   // 0: bf16 P/V   1: fp16 P/V, MUFU exp   2: fp16 P/V, 40% of the exponentials on the FMA pipe
 __global__ void __launch_bounds__(THREADS, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Params p) {
-  constexpr bool F16PV = MODE != 0;
+  constexpr bool F16PV = (MODE == 1 || MODE == 2);   // MODE 3: bf16 P/V with the chunked two-pass softmax
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_q = smem;                               // 2 tiles
@@ -222,6 +222,75 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Params p) {
     float l = 0.f;                                 // row sum (F16PV: kept in TMEM by the Ones MMA instead)
     uint32_t sph = 0;
 
+    if (MODE == 3) {
+      // ---- chunked two-pass variant (bf16 P/V): pass A reads S in 32-column chunks for the row max only, pass B
+      // re-reads each chunk, exponentiates, packs and stores it.  Only ~48 registers are live per chunk, so the
+      // scheduler can overlap the next chunk's TMEM load with the current chunk's MUFU/FMA work.
+      for (int j = 0; j < n_kv; ++j) {
+        mbar_wait(&s_full[t], sph);
+        sph ^= 1;
+        tc_fence_after();
+        const int kv_valid = p.S - j * BKV;
+        float m_tile = -INFINITY;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(s_addr + ch * 32, v);
+          tc_wait_ld();
+          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const float sv = (ch * 32 + c < kv_valid) ? __uint_as_float(v[c]) : -INFINITY;
+            m4[c & 3] = fmaxf(m4[c & 3], sv);
+          }
+          m_tile = fmaxf(m_tile, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+        }
+        const float m_new = fmaxf(m_used, m_tile);
+        const bool need = (m_new - m_used) > rescale_thresh;
+        if (__any_sync(0xffffffffu, need)) {
+          const float alpha = fast_exp2((m_used - m_new) * sl2);
+          l *= alpha;
+          m_used = m_new;
+          if (j > 0) {
+            uint32_t o0[32], o1[32];
+            tmem_ld_32x32b_x32(o_addr, o0);
+            tmem_ld_32x32b_x32(o_addr + 32, o1);
+            tc_wait_ld();
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              o0[c] = __float_as_uint(__uint_as_float(o0[c]) * alpha);
+              o1[c] = __float_as_uint(__uint_as_float(o1[c]) * alpha);
+            }
+            tmem_st_32x32b_x32(o_addr, o0);
+            tmem_st_32x32b_x32(o_addr + 32, o1);
+          }
+        }
+        const float neg_m = -m_used * sl2;
+        float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(s_addr + ch * 32, v);
+          tc_wait_ld();
+          uint32_t pk[16];
+#pragma unroll
+          for (int c = 0; c < 32; c += 2) {
+            float p0 = fast_exp2(fmaf(__uint_as_float(v[c]), sl2, neg_m));
+            float p1 = fast_exp2(fmaf(__uint_as_float(v[c + 1]), sl2, neg_m));
+            if (ch * 32 + c >= kv_valid) p0 = 0.f;
+            if (ch * 32 + c + 1 >= kv_valid) p1 = 0.f;
+            sum4[(c >> 1) & 3] += p0 + p1;
+            pk[c >> 1] = pack_bf16x2(p0, p1);
+          }
+          // P chunk ch occupies packed columns [16 ch, 16 ch + 16) of the aliased S region: already consumed
+          tmem_st_32x32b_x16(s_addr + ch * 16, pk);
+        }
+        l += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
+        tc_wait_st();
+        tc_fence_before();
+        mbar_arrive(&p_full[t]);
+      }
+    } else
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(&s_full[t], sph);
       sph ^= 1;
@@ -393,7 +462,8 @@ int attention_bf16(const void* qkv, void* out, int B, int S, int H, float softma
   switch (v_fp16) {
     case 0: return attn::launch<0>(tm, p, grid, stream);
     case 1: return attn::launch<1>(tm, p, grid, stream);
-    default: return attn::launch<2>(tm, p, grid, stream);
+    case 2: return attn::launch<2>(tm, p, grid, stream);
+    default: return attn::launch<3>(tm, p, grid, stream);   // 3: bf16 V, chunked softmax (v_fp16 is a mode id)
   }
 }
 

@@ -216,7 +216,7 @@ extern "C" int aether_dit_forward(AetherDit* h, const void* hidden_in, const voi
     RUN(ln_modulate(ws.hidden, ws.xn, B, S, St, D, lw.norm1_g, lw.norm1_b, c.norm_eps, nullptr, nullptr, m1, m1 + D,
                     m1 + 3 * D, m1 + 4 * D, mod_stride, stream));
     RUN(gemm_bf16(ws.xn, D, lw.w_qkv, D, ws.qkv, 3 * D, rows, 3 * D, D, lw.b_qkv, 0, nullptr, nullptr, 0, 0, 0,
-                  c.attention_fp16_pv ? 2 * D : -1, stream));
+                  (c.attention_fp16_pv == 1 || c.attention_fp16_pv == 2) ? 2 * D : -1, stream));
     RUN(qk_norm_rope(ws.qkv, B, S, St, c.num_heads, lw.qn_g, lw.qn_b, lw.kn_g, lw.kn_b, 1e-6f, rope_cos, rope_sin,
                      stream));
     if (h->timing) AETHER_CUDA_OK(cudaEventRecord(h->ev[2 * l], stream));

@@ -1,0 +1,336 @@
+// K9, bandwidth-bound half: GroupNorm / SpatialNorm3D + SiLU, nearest up-sampling, temporal
+// average pooling, layout conversions, posterior sampling and the tile blends of AutoencoderKLCogVideoX
+// (third-party diffusers module behind vae.encode / vae.decode, aetherv1_pipeline_cogvideox.py:557-620, :931, :936).
+// All tensors are channels-last  x[T, H, W, C]  bf16 unless stated; every kernel is a single streaming pass with
+// 16-byte vectors (8 channels per thread).  Algorithmic bytes are noted per kernel.
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace aether {
+
+__device__ __forceinline__ void unpack8v(const uint4& u, float (&f)[8]) {
+  f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+  f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8v(const float (&f)[8]) {
+  return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                    pack_bf16x2(f[6], f[7]));
+}
+__device__ __forceinline__ float bf16r(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm statistics over x[N, C] (N = T*H*W positions): per-block partial sums of every 4-channel quad in
+// a fixed order, then a single-block fp64 finalize -> mean[G], rstd[G].  Deterministic (no atomics).
+// Algorithmic bytes: N*C*2 read.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gn_partial_kernel(const __nv_bfloat16* __restrict__ x, int64_t N, int C, float* __restrict__ partial) {
+  // thread layout: tpr = C/8 threads per row; rows advance by (256 / tpr) * gridDim.x
+  const int tpr = C / 8;
+  const int lane_c = threadIdx.x % tpr;
+  const int row_in_blk = threadIdx.x / tpr;
+  const int rows_per_blk = 256 / tpr;
+  float s[2] = {0.f, 0.f}, q[2] = {0.f, 0.f};
+  for (int64_t r = int64_t(blockIdx.x) * rows_per_blk + row_in_blk; r < N; r += int64_t(gridDim.x) * rows_per_blk) {
+    float f[8];
+    unpack8v(*reinterpret_cast<const uint4*>(x + r * C + lane_c * 8), f);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      s[0] += f[j]; q[0] += f[j] * f[j];
+      s[1] += f[4 + j]; q[1] += f[4 + j] * f[4 + j];
+    }
+  }
+  extern __shared__ float red[];   // [256][4]
+  red[threadIdx.x * 4 + 0] = s[0]; red[threadIdx.x * 4 + 1] = q[0];
+  red[threadIdx.x * 4 + 2] = s[1]; red[threadIdx.x * 4 + 3] = q[1];
+  __syncthreads();
+  if (threadIdx.x < tpr) {         // fixed-order reduction over the rows handled by this block
+    float a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    for (int rr = 0; rr < rows_per_blk; ++rr) {
+      const float* p = red + (rr * tpr + threadIdx.x) * 4;
+      a0 += p[0]; a1 += p[1]; a2 += p[2]; a3 += p[3];
+    }
+    float* out = partial + (int64_t(blockIdx.x) * (C / 4) + threadIdx.x * 2) * 2;
+    out[0] = a0; out[1] = a1; out[2] = a2; out[3] = a3;
+  }
+}
+
+__global__ void gn_finalize_kernel(const float* __restrict__ partial, int nblocks, int C, int G, double count,
+                                   float eps, float* __restrict__ mean_rstd) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  const int quads_per_group = (C / G) / 4;
+  double s = 0.0, q = 0.0;
+  for (int b = 0; b < nblocks; ++b)
+    for (int k = 0; k < quads_per_group; ++k) {
+      const float* p = partial + (int64_t(b) * (C / 4) + g * quads_per_group + k) * 2;
+      s += p[0];
+      q += p[1];
+    }
+  const double mean = s / count;
+  const double var = fmax(q / count - mean * mean, 0.0);
+  mean_rstd[2 * g] = float(mean);
+  mean_rstd[2 * g + 1] = float(1.0 / sqrt(var + double(eps)));
+}
+
+// ------------------------------------------------------------------------------------------------
+// y = SiLU?( ((x - mean_g) * rstd_g * gamma_c + beta_c) [* zy[map(pos), c] + zb[map(pos), c]] )
+//   GroupNorm (encoder) or CogVideoXSpatialNorm3D (decoder; zy/zb = conv_y(zq)/conv_b(zq) evaluated at LATENT
+//   resolution -- a 1x1x1 conv commutes with nearest interpolation -- and gathered here by the nearest-neighbour
+//   index maps of F.interpolate).  Output rows may land inside a time-padded buffer (y is just a pointer).
+// Algorithmic bytes: 2*N*C*2 (+ the small zy/zb tables, L2-resident).
+// ------------------------------------------------------------------------------------------------
+struct GnApplyArgs {
+  const __nv_bfloat16* x;
+  __nv_bfloat16* y;
+  int64_t N;
+  int C, G;
+  const float* mean_rstd;
+  const float* gamma;
+  const float* beta;
+  const __nv_bfloat16* zy;     // nullable: [Tz, hz, wz, C]
+  const __nv_bfloat16* zb;
+  const int* tmap;             // [T] frame -> latent frame (device)
+  int H, W, hz, wz;
+  int silu;
+};
+
+__global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyArgs a) {
+  const int tpr = a.C / 8;
+  const int64_t total = a.N * tpr;
+  const int gs = a.C / a.G;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t r = i / tpr;
+    const int c0 = int(i - r * tpr) * 8;
+    float f[8];
+    unpack8v(*reinterpret_cast<const uint4*>(a.x + r * a.C + c0), f);
+    float gm[8], bt[8];
+    {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(a.gamma + c0));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(a.gamma + c0 + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.beta + c0));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(a.beta + c0 + 4));
+      gm[0] = g0.x; gm[1] = g0.y; gm[2] = g0.z; gm[3] = g0.w; gm[4] = g1.x; gm[5] = g1.y; gm[6] = g1.z; gm[7] = g1.w;
+      bt[0] = b0.x; bt[1] = b0.y; bt[2] = b0.z; bt[3] = b0.w; bt[4] = b1.x; bt[5] = b1.y; bt[6] = b1.z; bt[7] = b1.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int g = (c0 + j) / gs;
+      const float m = a.mean_rstd[2 * g], rs = a.mean_rstd[2 * g + 1];
+      f[j] = (f[j] - m) * rs * gm[j] + bt[j];
+    }
+    if (a.zy != nullptr) {
+      const int hw = a.H * a.W;
+      const int t = int(r / hw);
+      const int rem = int(r - int64_t(t) * hw);
+      const int yy = rem / a.W, xx = rem - yy * a.W;
+      const int64_t zr = (int64_t(a.tmap[t]) * a.hz + (yy * a.hz) / a.H) * a.wz + (xx * a.wz) / a.W;
+      float zy[8], zb[8];
+      unpack8v(__ldg(reinterpret_cast<const uint4*>(a.zy + zr * a.C + c0)), zy);
+      unpack8v(__ldg(reinterpret_cast<const uint4*>(a.zb + zr * a.C + c0)), zb);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = bf16r(f[j]) * zy[j] + zb[j];   // norm_f is a bf16 tensor upstream
+    }
+    if (a.silu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float v = bf16r(f[j]);                                   // activation input is the bf16 norm output
+        f[j] = v / (1.0f + __expf(-v));
+      }
+    }
+    *reinterpret_cast<uint4*>(a.y + r * a.C + c0) = pack8v(f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// out[t', y', x', :] = in[tmap[t'], y' / sy, x' / sx, :]      nearest up-sampling (F.interpolate) incl. the
+// "keep the first frame" temporal rule, which the host encodes in tmap.   Bytes: (1 + sy*sx*T'/T) * |in|.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+upsample_nearest_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const int* __restrict__ tmap, int To,
+                        int Ho, int Wo, int Hi, int Wi, int sy, int sx, int cvec) {
+  const int64_t total = int64_t(To) * Ho * Wo * cvec;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int cv = int(i % cvec);
+    int64_t r = i / cvec;
+    const int x = int(r % Wo); r /= Wo;
+    const int y = int(r % Ho);
+    const int t = int(r / Ho);
+    out[i] = __ldg(in + ((int64_t(tmap[t]) * Hi + y / sy) * Wi + x / sx) * cvec + cv);
+  }
+}
+
+// out[t'] = in[a[t']] if b[t'] < 0 else avg(in[a[t']], in[b[t']])   (F.avg_pool1d(k=2,s=2) keeping frame 0; bf16)
+__global__ void __launch_bounds__(256)
+avgpool_time_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const int* __restrict__ ia,
+                    const int* __restrict__ ib, int To, int64_t frame_vecs) {
+  const int64_t total = int64_t(To) * frame_vecs;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int t = int(i / frame_vecs);
+    const int64_t o = i - int64_t(t) * frame_vecs;
+    const uint4 va = __ldg(in + int64_t(ia[t]) * frame_vecs + o);
+    if (ib[t] < 0) {
+      out[i] = va;
+    } else {
+      float fa[8], fb[8];
+      unpack8v(va, fa);
+      unpack8v(__ldg(in + int64_t(ib[t]) * frame_vecs + o), fb);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) fa[j] = (fa[j] + fb[j]) * 0.5f;
+      out[i] = pack8v(fa);
+    }
+  }
+}
+
+// NCTHW [C, T, H, W] (one batch item, any of bf16) -> channels-last [T, H, W, Cp] with channels >= C zeroed.
+__global__ void __launch_bounds__(256)
+ncthw_to_thwc_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int C, int Cp,
+                     int64_t thw) {
+  const int64_t total = thw * Cp;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int c = int(i % Cp);
+    const int64_t p = i / Cp;
+    out[i] = c < C ? in[int64_t(c) * thw + p] : __float2bfloat16(0.f);
+  }
+}
+// channels-last [T*H*W, Cp] -> NCTHW [C, T*H*W] (first C channels)
+__global__ void __launch_bounds__(256)
+thwc_to_ncthw_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int C, int Cp,
+                     int64_t thw) {
+  const int64_t total = thw * C;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int c = int(i / thw);
+    const int64_t p = i - int64_t(c) * thw;
+    out[i] = in[p * Cp + c];
+  }
+}
+
+// DiagonalGaussianDistribution.sample: z = mean + exp(0.5 * clamp(logvar, -30, 20)) * noise, all bf16 tensors with
+// torch's roundings (each op's result is a bf16 tensor).  moments: channels-last [P, 2*L(+pad)], noise / z: NCTHW.
+__global__ void __launch_bounds__(256)
+posterior_sample_kernel(const __nv_bfloat16* __restrict__ moments, int Cp, int L, const __nv_bfloat16* __restrict__ noise,
+                        __nv_bfloat16* __restrict__ z, int64_t P, int use_noise) {
+  const int64_t total = P * L;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int c = int(i / P);
+    const int64_t p = i - int64_t(c) * P;
+    const float mean = __bfloat162float(moments[p * Cp + c]);
+    if (!use_noise) {
+      z[i] = __float2bfloat16_rn(mean);
+      continue;
+    }
+    float lv = __bfloat162float(moments[p * Cp + L + c]);
+    lv = fminf(fmaxf(lv, -30.f), 20.f);
+    const float stdv = bf16r(expf(bf16r(0.5f * lv)));
+    z[i] = __float2bfloat16_rn(mean + bf16r(stdv * __bfloat162float(noise[i])));
+  }
+}
+
+// blend_v / blend_h of the tiled VAE: b[.., k, ..] = a[.., La - extent + k, ..] * (1 - k/extent) + b[.., k, ..] * (k/extent)
+// for k < extent along `axis` (1 = rows, 2 = cols) of channels-last tiles a[T, Ha, Wa, C], b[T, Hb, Wb, C]; each product
+// and the sum are rounded to bf16 like the torch expression on bf16 tensors.
+__global__ void __launch_bounds__(256)
+tile_blend_kernel(const __nv_bfloat16* __restrict__ a, __nv_bfloat16* __restrict__ b, int T, int Ha, int Wa, int Hb,
+                  int Wb, int C, int axis, int extent) {
+  const int nh = axis == 1 ? extent : Hb, nw = axis == 2 ? extent : Wb;
+  const int64_t total = int64_t(T) * nh * nw * C;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int c = int(i % C);
+    int64_t r = i / C;
+    const int x = int(r % nw); r /= nw;
+    const int y = int(r % nh);
+    const int t = int(r / nh);
+    const int k = axis == 1 ? y : x;
+    const int ya = axis == 1 ? Ha - extent + y : y, xa = axis == 2 ? Wa - extent + x : x;
+    const float wa = 1.0f - float(double(k) / double(extent)), wb = float(double(k) / double(extent));
+    const float va = __bfloat162float(a[((int64_t(t) * Ha + ya) * Wa + xa) * C + c]);
+    __nv_bfloat16* pb = b + ((int64_t(t) * Hb + y) * Wb + x) * C + c;
+    *pb = __float2bfloat16_rn(bf16r(va * wa) + bf16r(__bfloat162float(*pb) * wb));
+  }
+}
+
+static unsigned sgrid(int64_t n) {
+  int64_t g = ceil_div(n, 256);
+  const int64_t cap = int64_t(num_sms()) * 16;
+  return (unsigned)(g > cap ? cap : (g < 1 ? 1 : g));
+}
+
+}  // namespace aether
+
+using namespace aether;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+#define BF(p) reinterpret_cast<__nv_bfloat16*>(p)
+#define CBF(p) reinterpret_cast<const __nv_bfloat16*>(p)
+extern "C" {
+
+int64_t aether_gn_workspace_floats(int32_t C) { return int64_t(num_sms()) * 4 * (C / 4) * 2; }
+
+int aether_gn_stats(const void* x, int64_t N, int32_t C, int32_t G, float eps, float* workspace, float* mean_rstd,
+                    void* stream) {
+  if (!x || !workspace || !mean_rstd || N <= 0 || C % 8 != 0 || C > 2048 || 256 % (C / 8) != 0 || C % G != 0 ||
+      (C / G) % 4 != 0)
+    return AETHER_ERR_INVALID;
+  const int rows_per_blk = 256 / (C / 8);
+  int nblocks = (int)ceil_div(N, rows_per_blk);
+  const int cap = num_sms() * 4;
+  if (nblocks > cap) nblocks = cap;
+  gn_partial_kernel<<<nblocks, 256, 256 * 4 * sizeof(float), ST(stream)>>>(CBF(x), N, C, workspace);
+  gn_finalize_kernel<<<(G + 63) / 64, 64, 0, ST(stream)>>>(workspace, nblocks, C, G, double(N) * (C / G), eps,
+                                                             mean_rstd);
+  return cudaGetLastError() == cudaSuccess ? AETHER_OK : AETHER_ERR_CUDA;
+}
+
+int aether_gn_apply(const void* x, void* y, int64_t N, int32_t C, int32_t G, const float* mean_rstd,
+                    const float* gamma, const float* beta, const void* zy, const void* zb, const int32_t* tmap,
+                    int32_t H, int32_t W, int32_t hz, int32_t wz, int32_t silu, void* stream) {
+  if (!x || !y || !mean_rstd || !gamma || !beta || N <= 0 || C % 8 != 0 || C % G != 0) return AETHER_ERR_INVALID;
+  if ((zy == nullptr) != (zb == nullptr) || (zy && (!tmap || H <= 0 || W <= 0 || hz <= 0 || wz <= 0)))
+    return AETHER_ERR_INVALID;
+  GnApplyArgs a{CBF(x), BF(y), N, C, G, mean_rstd, gamma, beta, CBF(zy), CBF(zb), tmap, H, W, hz, wz, silu};
+  gn_apply_kernel<<<sgrid(N * (C / 8)), 256, 0, ST(stream)>>>(a);
+  return cudaGetLastError() == cudaSuccess ? AETHER_OK : AETHER_ERR_CUDA;
+}
+
+int aether_upsample_nearest(const void* in, void* out, const int32_t* tmap, int32_t To, int32_t Ho, int32_t Wo,
+                            int32_t Hi, int32_t Wi, int32_t sy, int32_t sx, int32_t C, void* stream) {
+  if (!in || !out || !tmap || C % 8 != 0 || Ho != Hi * sy || Wo != Wi * sx) return AETHER_ERR_INVALID;
+  upsample_nearest_kernel<<<sgrid(int64_t(To) * Ho * Wo * (C / 8)), 256, 0, ST(stream)>>>(
+      reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), tmap, To, Ho, Wo, Hi, Wi, sy, sx, C / 8);
+  return cudaGetLastError() == cudaSuccess ? AETHER_OK : AETHER_ERR_CUDA;
+}
+
+int aether_avgpool_time(const void* in, void* out, const int32_t* ia, const int32_t* ib, int32_t To,
+                        int64_t frame_elems, void* stream) {
+  if (!in || !out || !ia || !ib || frame_elems % 8 != 0) return AETHER_ERR_INVALID;
+  avgpool_time_kernel<<<sgrid(int64_t(To) * frame_elems / 8), 256, 0, ST(stream)>>>(
+      reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), ia, ib, To, frame_elems / 8);
+  return cudaGetLastError() == cudaSuccess ? AETHER_OK : AETHER_ERR_CUDA;
+}
+
+int aether_ncthw_to_thwc(const void* in, void* out, int32_t C, int32_t Cp, int64_t thw, void* stream) {
+  if (!in || !out || C > Cp) return AETHER_ERR_INVALID;
+  ncthw_to_thwc_kernel<<<sgrid(thw * Cp), 256, 0, ST(stream)>>>(CBF(in), BF(out), C, Cp, thw);
+  return cudaGetLastError() == cudaSuccess ? AETHER_OK : AETHER_ERR_CUDA;
+}
+int aether_thwc_to_ncthw(const void* in, void* out, int32_t C, int32_t Cp, int64_t thw, void* stream) {
+  if (!in || !out || C > Cp) return AETHER_ERR_INVALID;
+  thwc_to_ncthw_kernel<<<sgrid(thw * C), 256, 0, ST(stream)>>>(CBF(in), BF(out), C, Cp, thw);
+  return cudaGetLastError() == cudaSuccess ? AETHER_OK : AETHER_ERR_CUDA;
+}
+int aether_posterior_sample(const void* moments, int32_t Cp, int32_t L, const void* noise, void* z, int64_t P,
+                            void* stream) {
+  if (!moments || !z || 2 * L > Cp) return AETHER_ERR_INVALID;
+  posterior_sample_kernel<<<sgrid(P * L), 256, 0, ST(stream)>>>(CBF(moments), Cp, L, CBF(noise), BF(z), P,
+                                                                noise != nullptr);
+  return cudaGetLastError() == cudaSuccess ? AETHER_OK : AETHER_ERR_CUDA;
+}
+int aether_tile_blend(const void* a, void* b, int32_t T, int32_t Ha, int32_t Wa, int32_t Hb, int32_t Wb, int32_t C,
+                      int32_t axis, int32_t extent, void* stream) {
+  if (!a || !b || (axis != 1 && axis != 2) || extent <= 0) return AETHER_ERR_INVALID;
+  if ((axis == 1 && (extent > Ha || extent > Hb || Wa != Wb)) || (axis == 2 && (extent > Wa || extent > Wb || Ha != Hb)))
+    return AETHER_ERR_INVALID;
+  const int64_t n = int64_t(T) * (axis == 1 ? extent : Hb) * (axis == 2 ? extent : Wb) * C;
+  tile_blend_kernel<<<sgrid(n), 256, 0, ST(stream)>>>(CBF(a), BF(b), T, Ha, Wa, Hb, Wb, C, axis, extent);
+  return cudaGetLastError() == cudaSuccess ? AETHER_OK : AETHER_ERR_CUDA;
+}
+}

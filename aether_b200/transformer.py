@@ -130,7 +130,7 @@ class AetherTransformer3D(nn.Module):
         self._n_layers_override = -1
         # kernel-mode switch (not a model hyper-parameter): fp16 P/V attention with ex2.f16x2 (default) or the
         # bf16 P/V variant; set before pack().
-        self.attention_fp16_pv = 2     # 0: bf16 P/V, 1: fp16 P/V (MUFU exp), 2: fp16 P/V + 40% polynomial exp
+        self.attention_fp16_pv = 0     # attention kernel mode 0..3, see csrc/attention_tcgen05.cu (0 measured fastest)
 
     # ------------------------------------------------------------------ torch plumbing
     @property

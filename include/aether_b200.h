@@ -153,6 +153,46 @@ int aether_dit_forward(AetherDit* h, const void* hidden, const void* text, const
                        int32_t W, int32_t St, void* workspace, int64_t workspace_bytes, int32_t n_layers,
                        void* stream);
 
+/* ---------------------------------------------------------------- 3-D causal VAE (K9)
+ * Device work behind AutoencoderKLCogVideoX.encode / .decode (pipeline :557-620, :931, :936).  Activations are
+ * channels-last x[T, H, W, C] bf16 (one batch item; the reference enables slicing).  The tiling / frame-batching
+ * / conv-cache control flow lives in aether_b200/vae.py and mirrors diffusers. */
+
+/* y[T_out,H_out,W_out,Cout] = conv(x[T_in,H_in,W_in,Cin], w) + bias (+ resid), implicit GEMM on tcgen05.
+ * x is time-padded by the caller (T_in = T_out + kt - 1); spatial zero padding of pad_h/pad_w leading rows/cols
+ * (trailing padding is implicit); stride 1 or 2 spatially.  w_packed: bf16 [Cout, kt*kh*kw*ceil64(Cin)], tap-major
+ * then channel, zero-padded channels.  Cin % 8 == 0, Cout % 8 == 0. */
+int aether_conv3d_bf16(const void* x, int32_t T_in, int32_t H_in, int32_t W_in, int32_t Cin, const void* w_packed,
+                       const float* bias, const void* resid, void* y, int32_t T_out, int32_t H_out, int32_t W_out,
+                       int32_t Cout, int32_t kt, int32_t kh, int32_t kw, int32_t stride, int32_t pad_h, int32_t pad_w,
+                       void* stream);
+/* GroupNorm statistics of x[N, C] (N = T*H*W): mean_rstd[2*G] = {mean_g, 1/sqrt(var_g + eps)}; deterministic.
+ * workspace: aether_gn_workspace_floats(C) floats. */
+int64_t aether_gn_workspace_floats(int32_t C);
+int aether_gn_stats(const void* x, int64_t N, int32_t C, int32_t G, float eps, float* workspace, float* mean_rstd,
+                    void* stream);
+/* y = SiLU?( GN(x) [* zy[map] + zb[map]] ): GroupNorm or CogVideoXSpatialNorm3D (zy/zb = conv_y/conv_b of the latent
+ * at latent resolution [Tz, hz, wz, C]; tmap[t] = latent frame of frame t; rows/cols map by floor(y*hz/H)). */
+int aether_gn_apply(const void* x, void* y, int64_t N, int32_t C, int32_t G, const float* mean_rstd,
+                    const float* gamma, const float* beta, const void* zy, const void* zb, const int32_t* tmap,
+                    int32_t H, int32_t W, int32_t hz, int32_t wz, int32_t silu, void* stream);
+/* out[t', y', x', :] = in[tmap[t'], y'/sy, x'/sx, :]   (F.interpolate nearest; first-frame rule encoded in tmap) */
+int aether_upsample_nearest(const void* in, void* out, const int32_t* tmap, int32_t To, int32_t Ho, int32_t Wo,
+                            int32_t Hi, int32_t Wi, int32_t sy, int32_t sx, int32_t C, void* stream);
+/* out[t'] = in[ia[t']] (ib[t'] < 0) or the mean of frames ia[t'], ib[t']   (temporal avg_pool1d keeping frame 0) */
+int aether_avgpool_time(const void* in, void* out, const int32_t* ia, const int32_t* ib, int32_t To,
+                        int64_t frame_elems, void* stream);
+/* layout conversions between the pipeline's NCTHW tensors and channels-last (Cp = padded channel count) */
+int aether_ncthw_to_thwc(const void* in, void* out, int32_t C, int32_t Cp, int64_t thw, void* stream);
+int aether_thwc_to_ncthw(const void* in, void* out, int32_t C, int32_t Cp, int64_t thw, void* stream);
+/* z (NCTHW [L, P]) = mean + exp(0.5*clamp(logvar,-30,20)) * noise from channels-last moments [P, Cp]
+ * (DiagonalGaussianDistribution.sample; noise NULL = mode()). */
+int aether_posterior_sample(const void* moments, int32_t Cp, int32_t L, const void* noise, void* z, int64_t P,
+                            void* stream);
+/* blend_v (axis 1) / blend_h (axis 2) of the tiled VAE, in place on b, bf16 roundings of the torch expression */
+int aether_tile_blend(const void* a, void* b, int32_t T, int32_t Ha, int32_t Wa, int32_t Hb, int32_t Wb, int32_t C,
+                      int32_t axis, int32_t extent, void* stream);
+
 /* ---------------------------------------------------------------- scheduler step (K8) */
 
 typedef struct AetherDpmCoeffs {

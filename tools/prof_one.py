@@ -8,8 +8,11 @@ n = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 g = torch.Generator(device="cuda").manual_seed(0)
 S, D, H = 15076, 3072, 48
 if which == "attention":
+    mode = int(sys.argv[3]) if len(sys.argv) > 3 else 2
     qkv = torch.randn(1, S, 3, H, 64, device="cuda", generator=g).bfloat16()
-    for _ in range(n): ops.attention(qkv)
+    if mode:
+        qkv.view(torch.float16)[:, :, 2] = qkv[:, :, 2].float().half()
+    for _ in range(n): ops.attention(qkv, v_fp16=mode)
 elif which == "gemm":
     a = torch.randn(S, D, device="cuda", generator=g).bfloat16()
     w = (torch.randn(4 * D, D, device="cuda", generator=g) / math.sqrt(D)).bfloat16()
