@@ -119,8 +119,10 @@ class AetherDPMScheduler:
 
     @staticmethod
     def _draw(sample, generator):
-        # diffusers.utils.torch_utils.randn_tensor(shape, generator, device=sample.device, dtype=sample.dtype)
-        return torch.randn(sample.shape, generator=generator, device=sample.device, dtype=sample.dtype)
+        # diffusers.utils.torch_utils.randn_tensor(shape, generator, device=sample.device, dtype=sample.dtype):
+        # a CPU generator draws on the CPU and the result is moved to the sample's device
+        gdev = generator.device if generator is not None else sample.device
+        return torch.randn(sample.shape, generator=generator, device=gdev, dtype=sample.dtype).to(sample.device)
 
     # ------------------------------------------------------------------ drop-in step (reference :907-915)
     @torch.no_grad()

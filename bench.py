@@ -12,8 +12,10 @@ A "step" is one pass of the denoise-loop body (reference aetherv1_pipeline_cogvi
 concat -> DiT forward (aether_dit_forward) -> fused CFG/DPM-Solver++ step (aether_cfg_dpm_step).  One 50-step
 generation yields 11 latent frames, so  value = N_gpus * 11 * (K / 50) / seconds.
   value : inputs resident in HBM, CUDA-event time over exactly K steps, max over ranks.
-  e2e   : the same step through the public modules with PINNED HOST buffers: per step the 96-channel model input
-          is copied host->device and the new latents device->host inside the timed region.
+  e2e   : the public API end to end: AetherV1PipelineCogVideoX.__call__(task="reconstruction", 41x480x720, 50
+          steps) with a HOST numpy video in and HOST numpy rgb/disparity/raymap out -- preprocessing, H2D, VAE
+          encode, the loop, 2x VAE decode and D2H inside the timed region (value = N * 11 / seconds per call);
+          `denoise_step_pinned_host` additionally reports the bare step with pinned host buffers.
   roofline : the attention kernel (dominant), duration from CUDA events recorded around every attention launch
           on the launching stream inside the timed region; algorithmic flop = 4*B*H*S^2*64 per launch.
   cpu_baseline / --impl reference : the reference's CPU path for this loop = the fp32 torch restatement of the
@@ -248,7 +250,48 @@ def run_product(args):
     e2e_ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_value = world * LATENT_FRAMES * (n_e2e / DENOISE_STEPS) / (float(e2e_ms.item()) / 1000.0)
+    e2e_step_value = world * LATENT_FRAMES * (n_e2e / DENOISE_STEPS) / (float(e2e_ms.item()) / 1000.0)
+    e2e = {"value": e2e_step_value, "unit": "latent-frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "steps": n_e2e, "scope": "denoise step via the public modules with pinned host buffers; VAE not included"}
+
+    # ---- e2e proper: the public API.  AetherV1PipelineCogVideoX.__call__ (reconstruction, 41 x 480 x 720, 50 steps)
+    # with a HOST numpy video in and HOST numpy rgb / disparity / raymap out: input preprocessing, H2D, VAE encode,
+    # the 50-step loop, 2 x VAE decode and D2H are all inside the timed region.
+    if not args.no_full_e2e:
+        import numpy as np
+        from aether_b200.pipeline import AetherV1PipelineCogVideoX
+        from aether_b200.vae import AetherVAE
+        vae = AetherVAE(device=dev)
+        vae.init_synthetic_(seed=1)
+        vae.enable_slicing()
+        vae.enable_tiling()
+        pipe = AetherV1PipelineCogVideoX(vae=vae, scheduler=AetherDPMScheduler(), transformer=model,
+                                         empty_prompt_embeds=text.cpu()).to(dev)
+        rng = np.random.default_rng(7 + rank)
+        video = rng.random((41, 480, 720, 3), dtype=np.float32)
+
+        def call(n):
+            return pipe(task="reconstruction", video=video, height=480, width=720, num_frames=41, fps=12,
+                        num_inference_steps=n, generator=torch.Generator(device=dev).manual_seed(42 + rank))
+
+        call(1)                                                     # warm-up call (VAE kernels, allocator)
+        barrier()
+        t0 = time.perf_counter()
+        out = call(DENOISE_STEPS)
+        torch.cuda.synchronize()
+        tc = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+        t_call = float(tc.item())
+        e2e = {"value": world * LATENT_FRAMES / t_call, "unit": "latent-frames/s",
+               "h2d_bytes_per_step": int(video.size * 2),
+               "d2h_bytes_per_step": int(out.rgb.nbytes + out.disparity.nbytes + out.raymap.nbytes),
+               "seconds_per_call": t_call, "calls": 1,
+               "scope": "AetherV1PipelineCogVideoX.__call__(reconstruction, 41x480x720, 50 steps): host numpy video -> "
+                        "preprocess -> H2D -> VAE encode -> 50 x (DiT + DPM step) -> 2 x VAE decode -> D2H numpy outputs "
+                        "(bytes are per call)",
+               "denoise_step_pinned_host": {"value": e2e_step_value, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                                            "steps": n_e2e}}
 
     if rank == 0:
         peak, peak_src = _peaks()
@@ -268,8 +311,7 @@ def run_product(args):
                        "denoise_steps": DENOISE_STEPS, "tokens": S_TOKENS, "attention_mode": int(model.attention_fp16_pv),
                        "parallelism": f"replicas x{world} (independent tiles per GPU, no data-path collective)",
                        "l2": "per-step working set (11.1 GB weights + ~1.4 GB activations) >> 126 MB L2; no explicit flush"},
-            "e2e": {"value": e2e_value, "unit": "latent-frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": n_e2e, "scope": "denoise step via the public modules with pinned host buffers; VAE encode/decode not included"},
+            "e2e": e2e,
             "gpu_launches": (model.launches_per_forward(1) + 1) * args.steps,
             "clocks": clocks,
             "roofline": {"kernel": "attention_kernel (tcgen05)", "bound": "tensor", "achieved": achieved, "peak": peak,
@@ -293,6 +335,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-full-e2e", action="store_true", help="skip the full pipeline __call__ e2e measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
