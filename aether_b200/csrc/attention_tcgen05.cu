@@ -442,6 +442,8 @@ static int launch(const CUtensorMap& tm, const Params& p, dim3 grid, cudaStream_
 
 }  // namespace attn
 
+int attention_v2_launch(const CUtensorMap& tm, int B, int S, int H, void* out, float scale_log2, cudaStream_t stream);
+
 // v_fp16 != 0: the V third of qkv holds fp16 values (GEMM f16_from_col) and an fp16-P mode runs:
 //   1 = every exponential on the MUFU, 2 = 40 % of them as an FMA-pipe polynomial (the product default).
 int attention_bf16(const void* qkv, void* out, int B, int S, int H, float softmax_scale, int v_fp16,
@@ -463,6 +465,7 @@ int attention_bf16(const void* qkv, void* out, int B, int S, int H, float softma
     case 0: return attn::launch<0>(tm, p, grid, stream);
     case 1: return attn::launch<1>(tm, p, grid, stream);
     case 2: return attn::launch<2>(tm, p, grid, stream);
+    case 4: return attention_v2_launch(tm, B, S, H, out, p.scale_log2, stream);   // 16 softmax warps (bf16 V)
     default: return attn::launch<3>(tm, p, grid, stream);   // 3: bf16 V, chunked softmax (v_fp16 is a mode id)
   }
 }
