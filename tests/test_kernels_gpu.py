@@ -92,7 +92,7 @@ def _attention_case(qkv_f32, v_fp16):
     return out, ref.transpose(1, 2).reshape(B, S, H * 64)
 
 
-@pytest.mark.parametrize("v_fp16", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("v_fp16", [0, 1, 2, 3, 4, 5])
 @pytest.mark.parametrize("B,S,H", [(1, 256, 2), (1, 128, 1), (2, 318, 4), (1, 1000, 2), (1, 4276, 4)])
 def test_attention(B, S, H, v_fp16):
     g = torch.Generator(device=DEV).manual_seed(S + H)
@@ -101,7 +101,7 @@ def test_attention(B, S, H, v_fp16):
     _close(out, ref, 2 ** -6, 1e-2, f"attention B{B} S{S} H{H} fp16={v_fp16}")
 
 
-@pytest.mark.parametrize("v_fp16", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("v_fp16", [0, 1, 2, 3, 4, 5])
 def test_attention_large_logits(v_fp16):
     """Rows whose running max grows by more than 2^8 between key tiles exercise the lazy O (and l) rescale."""
     g = torch.Generator(device=DEV).manual_seed(11)
@@ -113,7 +113,7 @@ def test_attention_large_logits(v_fp16):
     _close(out, ref, 2 ** -6, 2e-2, f"attention large logits fp16={v_fp16}")
 
 
-@pytest.mark.parametrize("v_fp16", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("v_fp16", [0, 1, 2, 3, 4, 5])
 def test_attention_peaked_and_flat_rows(v_fp16):
     """Nearly one-hot rows (large scale) and nearly uniform rows (tiny scale) in the same launch."""
     g = torch.Generator(device=DEV).manual_seed(12)
@@ -161,6 +161,24 @@ def test_ln_modulate(D):
     out2 = ops.ln_modulate(x, gamma, beta, 1e-5, sv, cv, St=0, gamma2=g2, beta2=b2, mod_bstride=4 * D)
     ref2 = torch.nn.functional.layer_norm(ln, (D,), g2, b2, 1e-5) * (1 + cv[:, None]) + sv[:, None]
     _close(out2, ref2, 2 ** -7, 1e-2, "double ln_modulate")
+
+
+@pytest.mark.parametrize("D,affine", [(256, True), (3072, True), (768, False)])
+def test_ln_modulate_persistent_path(D, affine):
+    """rows >= 1024 take the shared-memory-parameter persistent kernel (text and video segments, 2 batch items)."""
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(D + 1)
+    B, S, St = 2, 700, 226
+    x = (torch.randn(B, S, D, device=DEV, generator=g) * 1.5 - 0.2).bfloat16()
+    gamma = (1 + 0.1 * torch.randn(D, device=DEV, generator=g)) if affine else None
+    beta = (0.1 * torch.randn(D, device=DEV, generator=g)) if affine else None
+    mod = torch.randn(B, 4 * D, device=DEV, generator=g) * 0.3
+    sv, cv, st, ct = (mod[:, i * D:(i + 1) * D] for i in range(4))
+    out = ops.ln_modulate(x, gamma, beta, 1e-5, sv, cv, st, ct, St=St, mod_bstride=4 * D)
+    ln = torch.nn.functional.layer_norm(x.float(), (D,), gamma, beta, 1e-5)
+    is_t = (torch.arange(S, device=DEV) < St)[None, :, None]
+    ref = ln * (1 + torch.where(is_t, ct[:, None], cv[:, None])) + torch.where(is_t, st[:, None], sv[:, None])
+    _close(out, ref, 2 ** -7, 1e-2, "ln_modulate persistent")
 
 
 def test_qk_norm_rope():
