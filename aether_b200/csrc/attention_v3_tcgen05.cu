@@ -123,38 +123,49 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Params p
         for (int k = 0; k < BKV / 16; ++k)
           tc_mma_ts(o_col[t], p_col[t] + 8 * k, v_desc + 128 * k, idesc_pv, (!first || k > 0) ? 1u : 0u);
       };
-      int ks = 0, vs = 0;
-      uint32_t kph = 0, vph = 0;
+      // Skewed schedule: tile 1 runs HALF A PERIOD behind tile 0, so that one warpgroup is in its TMEM-load phase
+      // while the other is in its MUFU phase (both pipes deliver 16 elements/clk; in phase they would queue on
+      // the same pipe).  Per key tile j the MMA thread alternates
+      //   A (tile 0 has S_0(j) in registers):  QK_0(j+1)            then  PV_1(j-1)   [j == 0: the late QK_1(0)]
+      //   B (tile 1 has S_1(j) in registers):  QK_1(j+1)            then  PV_0(j)
+      // K(j+1) is released after QK_1(j+1), V(j) after PV_1(j) (one iteration later).
+      int ks = 0;                 // stage of K(j+1) inside the loop
+      uint32_t kph = 0;
+      int vs0 = 0, vs1 = 0;       // V stage of PV_0(j) / PV_1(j-1)
+      uint32_t vph0 = 0;
       mbar_wait(&k_full[0], 0);
       mbar_wait(&q_full[0], 0);
       tc_fence_after();
       issue_qk(0, 0);
       tc_commit(&s_full[0]);
-      mbar_wait(&q_full[1], 0);
-      tc_fence_after();
-      issue_qk(1, 0);
-      tc_commit(&s_full[1]);
-      tc_commit(&k_empty[0]);
       ks = 1;
       if (ks == KSTAGES) { ks = 0; kph ^= 1; }
       for (int j = 0; j < n_kv; ++j) {
         const bool last = (j + 1 == n_kv);
         const uint32_t ph = j & 1;
-        // ---- tile 0
+        // ---- phase A
         if (!last) {
           mbar_wait(&k_full[ks], kph);
-          mbar_wait(&s_free[0], ph);           // S_0(j) sits in registers
+          mbar_wait(&s_free[0], ph);
           tc_fence_after();
           issue_qk(0, ks);
           tc_commit(&s_full[0]);
         }
-        mbar_wait(&v_full[vs], vph);
-        mbar_wait(&p_full[0], ph);
-        tc_fence_after();
-        issue_pv(0, vs, j == 0);
-        tc_commit(&p_free[0]);
-        if (last) tc_commit(&o_full[0]);
-        // ---- tile 1
+        if (j == 0) {
+          mbar_wait(&q_full[1], 0);
+          tc_fence_after();
+          issue_qk(1, 0);                      // K(0) is still resident: stage 0
+          tc_commit(&s_full[1]);
+          tc_commit(&k_empty[0]);
+        } else {
+          mbar_wait(&p_full[1], (j - 1) & 1);
+          tc_fence_after();
+          issue_pv(1, vs1, j == 1);
+          tc_commit(&p_free[1]);
+          tc_commit(&v_empty[vs1]);
+          if (++vs1 == VSTAGES) vs1 = 0;
+        }
+        // ---- phase B
         if (!last) {
           mbar_wait(&s_free[1], ph);
           tc_fence_after();
@@ -163,14 +174,21 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Params p
           tc_commit(&k_empty[ks]);
           if (++ks == KSTAGES) { ks = 0; kph ^= 1; }
         }
-        mbar_wait(&p_full[1], ph);
+        mbar_wait(&v_full[vs0], vph0);
+        mbar_wait(&p_full[0], ph);
         tc_fence_after();
-        issue_pv(1, vs, j == 0);
-        tc_commit(&p_free[1]);
-        tc_commit(&v_empty[vs]);
-        if (last) tc_commit(&o_full[1]);
-        if (++vs == VSTAGES) { vs = 0; vph ^= 1; }
+        issue_pv(0, vs0, j == 0);
+        tc_commit(&p_free[0]);
+        if (last) tc_commit(&o_full[0]);
+        if (++vs0 == VSTAGES) { vs0 = 0; vph0 ^= 1; }
       }
+      // drain: PV_1(n-1)
+      mbar_wait(&p_full[1], (n_kv - 1) & 1);
+      tc_fence_after();
+      issue_pv(1, vs1, n_kv == 1);
+      tc_commit(&p_free[1]);
+      tc_commit(&v_empty[vs1]);
+      tc_commit(&o_full[1]);
     }
   } else {
     // ------------------------------------------------------------------ softmax warpgroups

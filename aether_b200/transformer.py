@@ -148,10 +148,25 @@ class AetherTransformer3D(nn.Module):
         return self.config.num_attention_heads * self.config.attention_head_dim
 
     def _apply(self, fn, *a, **k):
+        dev_before = self.proj_out.weight.device
         r = super()._apply(fn, *a, **k)
-        if self._handle is not None:      # parameters moved: packed buffers are stale
-            self.release()
+        if self._handle is not None and self.proj_out.weight.device != dev_before:
+            self.release()                # parameters moved to another device: packed buffers are stale
         return r
+
+    def to(self, *args, **kwargs):
+        """Moving an already packed module to the device it lives on is a no-op (pack(release_unpacked=True) drops
+        the unfused q/k/v weights, so a re-pack must never be triggered by `pipeline.to(same_device)`)."""
+        if self._handle is not None:
+            dev = None
+            for a in list(args) + list(kwargs.values()):
+                if isinstance(a, (str, torch.device)):
+                    dev = torch.device(a)
+            if dev is None or (dev.type == self.device.type and (dev.index is None or dev.index == self.device.index)):
+                return self
+            if getattr(self, "_released_unpacked", False):
+                raise RuntimeError("this module was packed with release_unpacked=True and cannot be moved")
+        return super().to(*args, **kwargs)
 
     def __del__(self):
         try:
@@ -273,6 +288,7 @@ class AetherTransformer3D(nn.Module):
         self._handle = h
         self._packed = P
         self._weights_struct = w
+        self._released_unpacked = bool(release_unpacked)
         return self
 
     def _pos_embedding_for(self, St, F, H, W):
