@@ -130,7 +130,8 @@ class AetherTransformer3D(nn.Module):
         self._n_layers_override = -1
         # kernel-mode switch (not a model hyper-parameter): fp16 P/V attention with ex2.f16x2 (default) or the
         # bf16 P/V variant; set before pack().
-        self.attention_fp16_pv = 0     # attention kernel mode 0..3, see csrc/attention_tcgen05.cu (0 measured fastest)
+        self.attention_fp16_pv = 5     # attention kernel mode 0..5 (csrc/attention*_tcgen05.cu); 5 = decoupled S/P
+        #                                buffers + skewed MMA schedule, measured fastest (3.76 ms vs 4.03 ms for mode 0)
 
     # ------------------------------------------------------------------ torch plumbing
     @property
