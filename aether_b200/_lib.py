@@ -73,6 +73,9 @@ SIGNATURES = {
     "aether_dit_workspace_bytes": (c_int64, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32]),
     "aether_dit_forward": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
                                      c_int32, c_int32, c_int32, c_int32, c_void_p, c_int64, c_int32, c_void_p]),
+    "aether_dit_forward_split": (C.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_void_p,
+                                           c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
+                                           c_int32, c_void_p, c_int64, c_int32, c_void_p]),
     "aether_conv3d_bf16": (C.c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
                                      c_int32, c_int32, c_void_p]),

@@ -26,8 +26,10 @@ int qk_norm_rope(void* qkv, int B, int S, int St, int H, const float* gq, const 
                  const float* bk, float eps, const float* cosb, const float* sinb, cudaStream_t stream);
 int small_m_linear(const float* x, const void* W, const float* bias, float* y, int B, int N, int K, int act,
                    cudaStream_t stream);
-int timestep_sinusoid(const int64_t* t, float* emb, int B, int dim, int flip, float shift, cudaStream_t stream);
-int patchify(const void* in, void* patches, int B, int F, int C, int H, int W, cudaStream_t stream);
+int timestep_sinusoid(const int64_t* t, int t_stride, float* emb, int B, int dim, int flip, float shift,
+                      cudaStream_t stream);
+int patchify2(const void* in0, int C0, int B0, const void* in1, int C1, void* patches, int B, int F, int H, int W,
+              cudaStream_t stream);
 int unpatchify(const void* tok, int64_t ld_tok, void* out, int B, int F, int C, int H, int W, cudaStream_t stream);
 int add_pos_embed(void* x, const void* pos, int B, int S, int D, cudaStream_t stream);
 }  // namespace aether
@@ -154,15 +156,20 @@ extern "C" int64_t aether_dit_workspace_bytes(const AetherDit* h, int32_t B, int
   return carve(h->cfg, B, S, nullptr).total + 256;
 }
 
-extern "C" int aether_dit_forward(AetherDit* h, const void* hidden_in, const void* text, const int64_t* timesteps,
-                                  const float* rope_cos, const float* rope_sin, void* out, int32_t B, int32_t F,
-                                  int32_t H, int32_t W, int32_t St, void* workspace, int64_t workspace_bytes,
-                                  int32_t n_layers, void* stream_) {
+// Model input = channel concat of in0[B0, F, C0, H, W] (B0 == 1: broadcast over the batch, the reference's
+// torch.cat([latents] * 2)) and in1[B, F, C1, H, W] (C1 may be 0); text [text_batch, St, dim] and timesteps
+// [timesteps_batch] broadcast when their batch is 1 (prompt_embeds.repeat / t.expand in the reference :862-869).
+static int dit_forward_impl(AetherDit* h, const void* in0, int C0, int B0, const void* in1, int C1, const void* text,
+                            int text_batch, const int64_t* timesteps, int timesteps_batch, const float* rope_cos,
+                            const float* rope_sin, void* out, int32_t B, int32_t F, int32_t H, int32_t W, int32_t St,
+                            void* workspace, int64_t workspace_bytes, int32_t n_layers, void* stream_) {
   using namespace aether;
-  if (!h || !hidden_in || !text || !timesteps || !out || !workspace) return AETHER_ERR_INVALID;
+  if (!h || !in0 || !text || !timesteps || !out || !workspace) return AETHER_ERR_INVALID;
   const AetherDitConfig& c = h->cfg;
   AETHER_CHECK_ARG(B > 0 && B <= 8 && F > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && St >= 0);
   AETHER_CHECK_ARG((rope_cos == nullptr) == (rope_sin == nullptr));
+  AETHER_CHECK_ARG(C0 + C1 == c.in_channels && (B0 == 1 || B0 == B) && (text_batch == 1 || text_batch == B) &&
+                   (timesteps_batch == 1 || timesteps_batch == B));
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const int D = c.num_heads * c.head_dim;
   const int T = c.time_embed_dim;
@@ -186,18 +193,20 @@ extern "C" int aether_dit_forward(AetherDit* h, const void* hidden_in, const voi
   } while (0)
 
   // ---- timestep embedding + every AdaLN modulation vector of this step
-  RUN(timestep_sinusoid(timesteps, ws.temb_sin, B, D, c.flip_sin_to_cos, c.freq_shift, stream));
+  RUN(timestep_sinusoid(timesteps, timesteps_batch == 1 ? 0 : 1, ws.temb_sin, B, D, c.flip_sin_to_cos, c.freq_shift,
+                        stream));
   RUN(small_m_linear(ws.temb_sin, h->w.w_time1, h->w.b_time1, ws.temb_h, B, T, D, 0, stream));
   RUN(small_m_linear(ws.temb_h, h->w.w_time2, h->w.b_time2, ws.temb, B, T, T, 1, stream));
   RUN(small_m_linear(ws.temb, h->w.w_adaln, h->w.b_adaln, ws.mod, B, (int)mod_stride, T, 1, stream));
 
   // ---- patch embed: text projection into rows [0, St), video patches into rows [St, S) of each batch
   char* patches = ws.ffh;   // [B*Sv, Kp] bf16 (ffh is free until the first FF1)
-  RUN(patchify(hidden_in, patches, B, F, c.in_channels, H, W, stream));
+  RUN(patchify2(in0, C0, B0, in1, C1, patches, B, F, H, W, stream));
   for (int b = 0; b < B; ++b) {
     char* hb = ws.hidden + int64_t(b) * S * D * 2;
     if (St > 0)
-      RUN(gemm_bf16(reinterpret_cast<const char*>(text) + int64_t(b) * St * c.text_embed_dim * 2, c.text_embed_dim,
+      RUN(gemm_bf16(reinterpret_cast<const char*>(text) + int64_t(text_batch == 1 ? 0 : b) * St * c.text_embed_dim * 2,
+                    c.text_embed_dim,
                     h->w.w_text, c.text_embed_dim, hb, D, St, D, c.text_embed_dim, h->w.b_text, 0, nullptr, nullptr,
                     0, 0, 0, -1, stream));
     RUN(gemm_bf16(patches + int64_t(b) * Sv * Kp * 2, Kp, h->w.w_patch, Kp, hb + int64_t(St) * D * 2, D, Sv, D, Kp,
@@ -246,4 +255,25 @@ extern "C" int aether_dit_forward(AetherDit* h, const void* hidden_in, const voi
   RUN(unpatchify(proj, Np, out, B, F, c.out_channels, H, W, stream));
 #undef RUN
   return AETHER_OK;
+}
+
+extern "C" int aether_dit_forward(AetherDit* h, const void* hidden_in, const void* text, const int64_t* timesteps,
+                                  const float* rope_cos, const float* rope_sin, void* out, int32_t B, int32_t F,
+                                  int32_t H, int32_t W, int32_t St, void* workspace, int64_t workspace_bytes,
+                                  int32_t n_layers, void* stream_) {
+  if (!h) return AETHER_ERR_INVALID;
+  return dit_forward_impl(h, hidden_in, h->cfg.in_channels, B, nullptr, 0, text, B, timesteps, B, rope_cos, rope_sin,
+                          out, B, F, H, W, St, workspace, workspace_bytes, n_layers, stream_);
+}
+
+extern "C" int aether_dit_forward_split(AetherDit* h, const void* latents, int32_t latents_batch,
+                                        int32_t latents_channels, const void* cond, const void* text,
+                                        int32_t text_batch, const int64_t* timesteps, int32_t timesteps_batch,
+                                        const float* rope_cos, const float* rope_sin, void* out, int32_t B, int32_t F,
+                                        int32_t H, int32_t W, int32_t St, void* workspace, int64_t workspace_bytes,
+                                        int32_t n_layers, void* stream_) {
+  if (!h || !cond) return AETHER_ERR_INVALID;
+  return dit_forward_impl(h, latents, latents_channels, latents_batch, cond, h->cfg.in_channels - latents_channels, text,
+                          text_batch, timesteps, timesteps_batch, rope_cos, rope_sin, out, B, F, H, W, St, workspace,
+                          workspace_bytes, n_layers, stream_);
 }

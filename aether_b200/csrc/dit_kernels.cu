@@ -440,14 +440,14 @@ int small_m_linear(const float* x, const void* W, const float* bias, float* y, i
 // ------------------------------------------------------------------------------------------------
 // diffusers get_timestep_embedding(scale=1, max_period=10000): emb = t * exp(-ln(1e4) * i / (half - shift)).
 // ------------------------------------------------------------------------------------------------
-__global__ void timestep_sinusoid_kernel(const int64_t* __restrict__ t, float* __restrict__ emb, int B, int dim,
-                                         int flip, float shift) {
+__global__ void timestep_sinusoid_kernel(const int64_t* __restrict__ t, int t_stride, float* __restrict__ emb, int B,
+                                         int dim, int flip, float shift) {
   const int half = dim / 2;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * half) return;
   const int b = idx / half, i = idx - b * half;
   const float freq = expf(-9.210340371976184f * float(i) / (float(half) - shift));
-  const float arg = float(t[b]) * freq;
+  const float arg = float(t[b * t_stride]) * freq;   // t_stride 0: one timestep broadcast over the batch
   const float sv = sinf(arg), cv = cosf(arg);
   float* e = emb + int64_t(b) * dim;
   if (flip) {
@@ -459,10 +459,11 @@ __global__ void timestep_sinusoid_kernel(const int64_t* __restrict__ t, float* _
   }
 }
 
-int timestep_sinusoid(const int64_t* t, float* emb, int B, int dim, int flip, float shift, cudaStream_t stream) {
-  AETHER_CHECK_ARG(B > 0 && dim > 0 && dim % 2 == 0);
+int timestep_sinusoid(const int64_t* t, int t_stride, float* emb, int B, int dim, int flip, float shift,
+                      cudaStream_t stream) {
+  AETHER_CHECK_ARG(B > 0 && dim > 0 && dim % 2 == 0 && (t_stride == 0 || t_stride == 1));
   const int n = B * dim / 2;
-  timestep_sinusoid_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(t, emb, B, dim, flip, shift);
+  timestep_sinusoid_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(t, t_stride, emb, B, dim, flip, shift);
   AETHER_CUDA_OK(cudaGetLastError());
   return AETHER_OK;
 }
@@ -473,18 +474,26 @@ int timestep_sinusoid(const int64_t* t, float* emb, int B, int dim, int flip, fl
 // One CTA per (b, f, y): the 2C image rows of the patch row are read coalesced (4-byte pairs) into shared
 // memory and written back as 16-byte vectors of the token-major layout.  Algorithmic bytes: 2 * |in|.
 // ------------------------------------------------------------------------------------------------
+// Two sources are concatenated along the channel axis on the fly (reference :832-859: cat([latents]*2) and
+// cat([latent_model_input, latent_condition], dim=2)): channels [0, C0) come from in0[B0, F, C0, H, W] (B0 == 1
+// broadcasts the latents over the CFG batch), channels [C0, C0+C1) from in1[B, F, C1, H, W].  C1 == 0: single source.
 __global__ void __launch_bounds__(256)
-patchify_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int C, int H, int W) {
+patchify_kernel(const __nv_bfloat16* __restrict__ in0, int C0, int B0, const __nv_bfloat16* __restrict__ in1, int C1,
+                __nv_bfloat16* __restrict__ out, int F, int H, int W) {
   extern __shared__ uint32_t tile[];   // [2C][W/2] pairs
+  const int C = C0 + C1;
   const int Wp = W / 2, Hp = H / 2;
   const int y = blockIdx.x % Hp;
   const int bf = blockIdx.x / Hp;
-  const uint32_t* src = reinterpret_cast<const uint32_t*>(in + int64_t(bf) * C * H * W);
+  const int b = bf / F, f = bf - b * F;
+  const uint32_t* src0 = reinterpret_cast<const uint32_t*>(in0 + (int64_t(B0 == 1 ? 0 : b) * F + f) * C0 * H * W);
+  const uint32_t* src1 = C1 ? reinterpret_cast<const uint32_t*>(in1 + (int64_t(b) * F + f) * C1 * H * W) : nullptr;
   const int npairs = 2 * C * Wp;
   for (int i = threadIdx.x; i < npairs; i += blockDim.x) {
     const int r = i / Wp, xp = i - r * Wp;           // r = c*2 + dy
     const int c = r >> 1, dy = r & 1;
-    tile[i] = src[(int64_t(c) * H + 2 * y + dy) * Wp + xp];
+    tile[i] = c < C0 ? src0[(int64_t(c) * H + 2 * y + dy) * Wp + xp]
+                     : src1[(int64_t(c - C0) * H + 2 * y + dy) * Wp + xp];
   }
   __syncthreads();
   uint32_t* dst = reinterpret_cast<uint32_t*>(out + (int64_t(bf) * Hp + y) * Wp * (C * 4));
@@ -494,8 +503,11 @@ patchify_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict_
   }
 }
 
-int patchify(const void* in, void* patches, int B, int F, int C, int H, int W, cudaStream_t stream) {
-  AETHER_CHECK_ARG(B > 0 && F > 0 && C > 0 && H % 2 == 0 && W % 2 == 0);
+int patchify2(const void* in0, int C0, int B0, const void* in1, int C1, void* patches, int B, int F, int H, int W,
+              cudaStream_t stream) {
+  const int C = C0 + C1;
+  AETHER_CHECK_ARG(B > 0 && F > 0 && C0 > 0 && C1 >= 0 && H % 2 == 0 && W % 2 == 0 && in0 && (C1 == 0 || in1));
+  AETHER_CHECK_ARG(B0 == 1 || B0 == B);
   const size_t smem = size_t(2) * C * (W / 2) * 4;
   AETHER_CHECK_ARG(smem <= 160 * 1024);
   static size_t smem_set = 0;
@@ -504,9 +516,14 @@ int patchify(const void* in, void* patches, int B, int F, int C, int H, int W, c
     smem_set = smem;
   }
   patchify_kernel<<<(unsigned)(B * F * (H / 2)), 256, smem, stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(in), reinterpret_cast<__nv_bfloat16*>(patches), C, H, W);
+      reinterpret_cast<const __nv_bfloat16*>(in0), C0, B0, reinterpret_cast<const __nv_bfloat16*>(in1), C1,
+      reinterpret_cast<__nv_bfloat16*>(patches), F, H, W);
   AETHER_CUDA_OK(cudaGetLastError());
   return AETHER_OK;
+}
+
+int patchify(const void* in, void* patches, int B, int F, int C, int H, int W, cudaStream_t stream) {
+  return patchify2(in, C, B, nullptr, 0, patches, B, F, H, W, stream);
 }
 
 // K7 back half: inverse of the above for the proj_out tokens:  out[b,f,c,2y+dy,2x+dx] = tok[(b,f,y,x), c*4+dy*2+dx]
@@ -593,7 +610,7 @@ int aether_small_m_linear(const float* x, const void* W, const float* bias, floa
 }
 int aether_timestep_sinusoid(const int64_t* timesteps, float* emb, int32_t B, int32_t dim, int32_t flip_sin_to_cos,
                              float freq_shift, void* stream) {
-  return timestep_sinusoid(timesteps, emb, B, dim, flip_sin_to_cos, freq_shift, ST(stream));
+  return timestep_sinusoid(timesteps, 1, emb, B, dim, flip_sin_to_cos, freq_shift, ST(stream));
 }
 int aether_patchify(const void* in, void* patches, int32_t B, int32_t F, int32_t C, int32_t H, int32_t W,
                     void* stream) {

@@ -473,6 +473,9 @@ class AetherV1PipelineCogVideoX:
         n_cfg = 2 if do_cfg else 1
         text = prompt_embeds.repeat(n_cfg, 1, 1)
         fused = hasattr(self.scheduler, "step_fused")
+        # with the aether_b200 transformer the concat / repeat / expand of :832-869 happen inside the patch-gather
+        # kernel (aether_dit_forward_split): the loop body is then exactly two C-ABI calls
+        split = fused and hasattr(self.transformer, "forward_split") and ofs_emb is None
         num_warmup_steps = max(len(timesteps) - num_inference_steps * self.scheduler.order, 0)
 
         with self.progress_bar(total=num_inference_steps) as progress_bar:
@@ -481,13 +484,17 @@ class AetherV1PipelineCogVideoX:
                 if self.interrupt:
                     continue
                 self._current_timestep = t
-                lmi = torch.cat([latents] * 2) if do_cfg else latents
-                lmi = self.scheduler.scale_model_input(lmi, t)
-                lmi = torch.cat([lmi, latent_condition], dim=2)
-                timestep = t.expand(lmi.shape[0])
-                noise_pred = self.transformer(hidden_states=lmi, encoder_hidden_states=text, timestep=timestep,
-                                              ofs=ofs_emb, image_rotary_emb=image_rotary_emb,
-                                              attention_kwargs=attention_kwargs, return_dict=False)[0]
+                if split:
+                    noise_pred = self.transformer.forward_split(latents, latent_condition, prompt_embeds, t.reshape(1),
+                                                                image_rotary_emb)
+                else:
+                    lmi = torch.cat([latents] * 2) if do_cfg else latents
+                    lmi = self.scheduler.scale_model_input(lmi, t)
+                    lmi = torch.cat([lmi, latent_condition], dim=2)
+                    timestep = t.expand(lmi.shape[0])
+                    noise_pred = self.transformer(hidden_states=lmi, encoder_hidden_states=text, timestep=timestep,
+                                                  ofs=ofs_emb, image_rotary_emb=image_rotary_emb,
+                                                  attention_kwargs=attention_kwargs, return_dict=False)[0]
                 if use_dynamic_cfg:   # :879-893, python-float arithmetic on the raw timestep value
                     self._guidance_scale = 1 + guidance_scale * (
                         (1 - math.cos(math.pi * ((num_inference_steps - t_host[i]) / num_inference_steps) ** 5.0)) / 2)

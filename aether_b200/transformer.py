@@ -330,6 +330,41 @@ class AetherTransformer3D(nn.Module):
         """Kernels of this library launched by one forward (see csrc/dit_forward.cu)."""
         return 4 + 1 + 2 * batch + 8 * self.config.num_layers + 1 + batch + 1
 
+    # ------------------------------------------------------------------ loop form: concat / repeat / expand folded in
+    @torch.no_grad()
+    def forward_split(self, latents: torch.Tensor, condition: torch.Tensor, encoder_hidden_states: torch.Tensor,
+                      timestep: torch.Tensor, image_rotary_emb=None):
+        """Reference :832-875 in one C-ABI call: `latents` [1 or B, F, C0, H, W] is broadcast over the batch of
+        `condition` [B, F, C1, H, W] and concatenated along channels inside the patch-gather kernel; the prompt
+        embedding [1 or B, St, dim] and the timestep [1 or B] broadcast likewise.  Returns [B, F, out, H, W] bf16."""
+        lib = _lib.require_device()
+        if self._handle is None:
+            self.pack()
+        c = self.config
+        B, F, C1, H, W = condition.shape
+        Bl, _, C0, _, _ = latents.shape
+        assert C0 + C1 == c.in_channels and latents.is_cuda
+        lat = latents.to(torch.bfloat16).contiguous()
+        cond = condition.to(torch.bfloat16).contiguous()
+        txt = encoder_hidden_states.to(torch.bfloat16).contiguous()
+        ts = timestep.to(device=lat.device, dtype=torch.int64).reshape(-1).contiguous()
+        St = txt.shape[1]
+        cos = sin = None
+        if image_rotary_emb is not None:
+            cos = image_rotary_emb[0].to(device=lat.device, dtype=torch.float32).contiguous()
+            sin = image_rotary_emb[1].to(device=lat.device, dtype=torch.float32).contiguous()
+        check(lib.aether_dit_set_pos_embedding(self._handle, ptr(self._pos_embedding_for(St, F, H, W))),
+              "dit_set_pos_embedding")
+        need = lib.aether_dit_workspace_bytes(self._handle, B, F, H, W, St)
+        if self._ws is None or self._ws.numel() < need or self._ws.device != lat.device:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=lat.device)
+        out = torch.empty(B, F, c.out_channels, H, W, dtype=torch.bfloat16, device=lat.device)
+        check(lib.aether_dit_forward_split(self._handle, ptr(lat), Bl, C0, ptr(cond), ptr(txt), txt.shape[0], ptr(ts),
+                                           ts.numel(), ptr(cos), ptr(sin), ptr(out), B, F, H, W, St, ptr(self._ws),
+                                           self._ws.numel(), self._n_layers_override, current_stream()),
+              "dit_forward_split")
+        return out
+
     # ------------------------------------------------------------------ forward = one C-ABI call
     @torch.no_grad()
     def forward(self, hidden_states: torch.Tensor, encoder_hidden_states: torch.Tensor, timestep: torch.Tensor,

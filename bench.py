@@ -193,8 +193,8 @@ def run_product(args):
         if k == 0:
             state["old"] = None
         lat = state["latents"] if lat_in is None else lat_in
-        lmi = torch.cat([lat, cond], dim=2)
-        out = model(lmi, text, sched.timesteps[k].expand(1), image_rotary_emb=rope)[0]
+        # the 96-channel concat of reference :857 happens inside the patch-gather kernel (aether_dit_forward_split)
+        out = model.forward_split(lat, cond, text, sched.timesteps[k].reshape(1), rope)
         new, state["old"] = sched.step_fused(out, 1.0, state["old"], t_host[k], t_host[k - 1] if k > 0 else None, lat,
                                              generator=noise_gen)
         state["latents"] = new

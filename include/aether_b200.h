@@ -153,6 +153,16 @@ int aether_dit_forward(AetherDit* h, const void* hidden, const void* text, const
                        int32_t W, int32_t St, void* workspace, int64_t workspace_bytes, int32_t n_layers,
                        void* stream);
 
+/* Same forward with the loop's concatenations folded in (pipeline :832-869): the model input is the channel concat
+ * of latents[latents_batch, F, latents_channels, H, W] (latents_batch == 1 broadcasts over the CFG batch =
+ * torch.cat([latents] * 2)) and cond[B, F, in_channels - latents_channels, H, W]; text [text_batch, St, dim] and
+ * timesteps [timesteps_batch] broadcast when their batch is 1 (prompt_embeds.repeat, t.expand). */
+int aether_dit_forward_split(AetherDit* h, const void* latents, int32_t latents_batch, int32_t latents_channels,
+                             const void* cond, const void* text, int32_t text_batch, const int64_t* timesteps,
+                             int32_t timesteps_batch, const float* rope_cos, const float* rope_sin, void* out,
+                             int32_t B, int32_t F, int32_t H, int32_t W, int32_t St, void* workspace,
+                             int64_t workspace_bytes, int32_t n_layers, void* stream);
+
 /* ---------------------------------------------------------------- 3-D causal VAE (K9)
  * Device work behind AutoencoderKLCogVideoX.encode / .decode (pipeline :557-620, :931, :936).  Activations are
  * channels-last x[T, H, W, C] bf16 (one batch item; the reference enables slicing).  The tiling / frame-batching

@@ -74,6 +74,21 @@ def test_dit_forward_wider_model():
     _check(out, ref, "dit forward D=768")
 
 
+def test_forward_split_equals_concat_forward():
+    """aether_dit_forward_split (latents broadcast over the CFG batch + condition, prompt and timestep broadcast)
+    must be bit-identical to the reference-shaped call on the explicitly concatenated / repeated tensors."""
+    cfg, oracle, model = _build({})
+    x, e, cos, sin = _inputs(cfg, 2, 5, 12, 20)
+    lat = x[:1, :, :cfg.out_channels].contiguous().cuda()
+    cond = x[:, :, cfg.out_channels:].contiguous().cuda()
+    t = torch.tensor([499], dtype=torch.int64).cuda()
+    rope = (cos.cuda(), sin.cuda())
+    ref = model(torch.cat([torch.cat([lat] * 2), cond], dim=2), e[:1].cuda().repeat(2, 1, 1), t.expand(2),
+                image_rotary_emb=rope)[0]
+    got = model.forward_split(lat, cond, e[:1].cuda(), t, rope)
+    assert torch.equal(ref, got)
+
+
 def test_dit_forward_deterministic():
     cfg, oracle, model = _build({})
     x, e, cos, sin = _inputs(cfg, 1, 5, 12, 20)
