@@ -82,7 +82,8 @@ SIGNATURES = {
     "aether_gn_workspace_floats": (c_int64, [c_int32]),
     "aether_gn_stats": (C.c_int, [c_void_p, c_int64, c_int32, c_int32, c_float, c_void_p, c_void_p, c_void_p]),
     "aether_gn_apply": (C.c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
-                                  c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+                                  c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                  c_void_p]),
     "aether_upsample_nearest": (C.c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
                                           c_int32, c_int32, c_int32, c_void_p]),
     "aether_avgpool_time": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_void_p]),

@@ -31,9 +31,28 @@ gn_partial_kernel(const __nv_bfloat16* __restrict__ x, int64_t N, int C, float* 
   const int row_in_blk = threadIdx.x / tpr;
   const int rows_per_blk = 256 / tpr;
   float s[2] = {0.f, 0.f}, q[2] = {0.f, 0.f};
-  for (int64_t r = int64_t(blockIdx.x) * rows_per_blk + row_in_blk; r < N; r += int64_t(gridDim.x) * rows_per_blk) {
+  const int64_t stride = int64_t(gridDim.x) * rows_per_blk;
+  int64_t r = int64_t(blockIdx.x) * rows_per_blk + row_in_blk;
+  // 4 independent 16-byte loads in flight per thread (the loop is pure streaming; one dependent load per
+  // iteration left the kernel latency-bound)
+  for (; r + 3 * stride < N; r += 4 * stride) {
+    uint4 u[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(x + (r + k * stride) * C + lane_c * 8));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float f[8];
+      unpack8v(u[k], f);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        s[0] += f[j]; q[0] += f[j] * f[j];
+        s[1] += f[4 + j]; q[1] += f[4 + j] * f[4 + j];
+      }
+    }
+  }
+  for (; r < N; r += stride) {
     float f[8];
-    unpack8v(*reinterpret_cast<const uint4*>(x + r * C + lane_c * 8), f);
+    unpack8v(__ldg(reinterpret_cast<const uint4*>(x + r * C + lane_c * 8)), f);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       s[0] += f[j]; q[0] += f[j] * f[j];
@@ -55,22 +74,34 @@ gn_partial_kernel(const __nv_bfloat16* __restrict__ x, int64_t N, int C, float* 
   }
 }
 
-__global__ void gn_finalize_kernel(const float* __restrict__ partial, int nblocks, int C, int G, double count,
-                                   float eps, float* __restrict__ mean_rstd) {
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= G) return;
+// one warp per group: lane-strided fp64 accumulation over the block partials in a fixed order + shuffle tree
+// (deterministic); the previous one-thread-per-group serial loop took longer than the streaming pass itself.
+__global__ void __launch_bounds__(1024)
+gn_finalize_kernel(const float* __restrict__ partial, int nblocks, int C, int G, double count, float eps,
+                   float* __restrict__ mean_rstd) {
+  const int lane = threadIdx.x & 31;
   const int quads_per_group = (C / G) / 4;
-  double s = 0.0, q = 0.0;
-  for (int b = 0; b < nblocks; ++b)
-    for (int k = 0; k < quads_per_group; ++k) {
-      const float* p = partial + (int64_t(b) * (C / 4) + g * quads_per_group + k) * 2;
-      s += p[0];
-      q += p[1];
+  for (int g = threadIdx.x >> 5; g < G; g += blockDim.x >> 5) {
+    double s = 0.0, q = 0.0;
+    const int n = nblocks * quads_per_group;
+    for (int i = lane; i < n; i += 32) {
+      const int b = i / quads_per_group, k = i - b * quads_per_group;
+      const float2 p = *reinterpret_cast<const float2*>(partial + (int64_t(b) * (C / 4) + g * quads_per_group + k) * 2);
+      s += p.x;
+      q += p.y;
     }
-  const double mean = s / count;
-  const double var = fmax(q / count - mean * mean, 0.0);
-  mean_rstd[2 * g] = float(mean);
-  mean_rstd[2 * g + 1] = float(1.0 / sqrt(var + double(eps)));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if (lane == 0) {
+      const double mean = s / count;
+      const double var = fmax(q / count - mean * mean, 0.0);
+      mean_rstd[2 * g] = float(mean);
+      mean_rstd[2 * g + 1] = float(1.0 / sqrt(var + double(eps)));
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -92,6 +123,7 @@ struct GnApplyArgs {
   const __nv_bfloat16* zb;
   const int* tmap;             // [T] frame -> latent frame (device)
   int H, W, hz, wz;
+  int zld;                     // row stride (elements) of the zy / zb tables
   int silu;
 };
 
@@ -99,11 +131,22 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyArgs a) {
   const int tpr = a.C / 8;
   const int64_t total = a.N * tpr;
   const int gs = a.C / a.G;
-  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+  const int64_t gstride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t i0 = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i0 < total; i0 += 4 * gstride) {
+    uint4 xin[4];                     // 4 independent 16-byte loads in flight before any dependent work / store
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int64_t i = i0 + k * gstride;
+      if (i < total) xin[k] = __ldg(reinterpret_cast<const uint4*>(a.x) + i);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+    const int64_t i = i0 + k * gstride;
+    if (i >= total) break;
     const int64_t r = i / tpr;
     const int c0 = int(i - r * tpr) * 8;
     float f[8];
-    unpack8v(*reinterpret_cast<const uint4*>(a.x + r * a.C + c0), f);
+    unpack8v(xin[k], f);
     float gm[8], bt[8];
     {
       const float4 g0 = __ldg(reinterpret_cast<const float4*>(a.gamma + c0));
@@ -126,8 +169,8 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyArgs a) {
       const int yy = rem / a.W, xx = rem - yy * a.W;
       const int64_t zr = (int64_t(a.tmap[t]) * a.hz + (yy * a.hz) / a.H) * a.wz + (xx * a.wz) / a.W;
       float zy[8], zb[8];
-      unpack8v(__ldg(reinterpret_cast<const uint4*>(a.zy + zr * a.C + c0)), zy);
-      unpack8v(__ldg(reinterpret_cast<const uint4*>(a.zb + zr * a.C + c0)), zb);
+      unpack8v(__ldg(reinterpret_cast<const uint4*>(a.zy + zr * a.zld + c0)), zy);
+      unpack8v(__ldg(reinterpret_cast<const uint4*>(a.zb + zr * a.zld + c0)), zb);
 #pragma unroll
       for (int j = 0; j < 8; ++j) f[j] = bf16r(f[j]) * zy[j] + zb[j];   // norm_f is a bf16 tensor upstream
     }
@@ -139,6 +182,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyArgs a) {
       }
     }
     *reinterpret_cast<uint4*>(a.y + r * a.C + c0) = pack8v(f);
+    }
   }
 }
 
@@ -263,7 +307,7 @@ using namespace aether;
 #define CBF(p) reinterpret_cast<const __nv_bfloat16*>(p)
 extern "C" {
 
-int64_t aether_gn_workspace_floats(int32_t C) { return int64_t(num_sms()) * 4 * (C / 4) * 2; }
+int64_t aether_gn_workspace_floats(int32_t C) { return int64_t(num_sms()) * 8 * (C / 4) * 2; }
 
 int aether_gn_stats(const void* x, int64_t N, int32_t C, int32_t G, float eps, float* workspace, float* mean_rstd,
                     void* stream) {
@@ -272,22 +316,22 @@ int aether_gn_stats(const void* x, int64_t N, int32_t C, int32_t G, float eps, f
     return AETHER_ERR_INVALID;
   const int rows_per_blk = 256 / (C / 8);
   int nblocks = (int)ceil_div(N, rows_per_blk);
-  const int cap = num_sms() * 4;
+  const int cap = num_sms() * 8;       // 8 resident blocks of 256 threads per SM
   if (nblocks > cap) nblocks = cap;
   gn_partial_kernel<<<nblocks, 256, 256 * 4 * sizeof(float), ST(stream)>>>(CBF(x), N, C, workspace);
-  gn_finalize_kernel<<<(G + 63) / 64, 64, 0, ST(stream)>>>(workspace, nblocks, C, G, double(N) * (C / G), eps,
-                                                             mean_rstd);
+  const int fin_threads = G * 32 < 1024 ? G * 32 : 1024;      // one warp per group
+  gn_finalize_kernel<<<1, fin_threads, 0, ST(stream)>>>(workspace, nblocks, C, G, double(N) * (C / G), eps, mean_rstd);
   return cudaGetLastError() == cudaSuccess ? AETHER_OK : AETHER_ERR_CUDA;
 }
 
 int aether_gn_apply(const void* x, void* y, int64_t N, int32_t C, int32_t G, const float* mean_rstd,
-                    const float* gamma, const float* beta, const void* zy, const void* zb, const int32_t* tmap,
-                    int32_t H, int32_t W, int32_t hz, int32_t wz, int32_t silu, void* stream) {
+                    const float* gamma, const float* beta, const void* zy, const void* zb, int32_t zld,
+                    const int32_t* tmap, int32_t H, int32_t W, int32_t hz, int32_t wz, int32_t silu, void* stream) {
   if (!x || !y || !mean_rstd || !gamma || !beta || N <= 0 || C % 8 != 0 || C % G != 0) return AETHER_ERR_INVALID;
   if ((zy == nullptr) != (zb == nullptr) || (zy && (!tmap || H <= 0 || W <= 0 || hz <= 0 || wz <= 0)))
     return AETHER_ERR_INVALID;
-  GnApplyArgs a{CBF(x), BF(y), N, C, G, mean_rstd, gamma, beta, CBF(zy), CBF(zb), tmap, H, W, hz, wz, silu};
-  gn_apply_kernel<<<sgrid(N * (C / 8)), 256, 0, ST(stream)>>>(a);
+  GnApplyArgs a{CBF(x), BF(y), N, C, G, mean_rstd, gamma, beta, CBF(zy), CBF(zb), tmap, H, W, hz, wz, zld > 0 ? zld : C, silu};
+  gn_apply_kernel<<<sgrid(ceil_div(N * (C / 8), 4)), 256, 0, ST(stream)>>>(a);
   return cudaGetLastError() == cudaSuccess ? AETHER_OK : AETHER_ERR_CUDA;
 }
 

@@ -255,10 +255,12 @@ class AetherVAE(nn.Module):
 
         def spatial(name, m):
             gn(name + ".norm_layer", m.norm_layer)
-            for nm in ("conv_y", "conv_b"):
-                cm = getattr(m, nm).conv
-                P[f"{name}.{nm}"] = dict(w=cm.weight.detach().reshape(cm.weight.shape[0], -1).to(dev, BF16).contiguous(),
-                                         b=cm.bias.detach().to(dev, torch.float32).contiguous())
+            # conv_y | conv_b (1x1x1 on the latent) fused row-wise: ONE GEMM yields [N_z, 2C] = (scale | bias)
+            wy, wb = m.conv_y.conv, m.conv_b.conv
+            P[name + ".conv_yb"] = dict(
+                w=torch.cat([wy.weight.detach().reshape(wy.weight.shape[0], -1),
+                             wb.weight.detach().reshape(wb.weight.shape[0], -1)], dim=0).to(dev, BF16).contiguous(),
+                b=torch.cat([wy.bias.detach(), wb.bias.detach()]).to(dev, torch.float32).contiguous())
 
         def resnet(name, m, spatial_norm):
             (spatial if spatial_norm else gn)(name + ".norm1", m.norm1)
@@ -328,20 +330,20 @@ class AetherVAE(nn.Module):
         assert out.is_contiguous() and out.shape == x.shape
         if zq is None:
             p = self._packed[name]
-            check(lib.aether_gn_apply(ptr(x), ptr(out), N, C, G, ptr(mr), ptr(p["g"]), ptr(p["b"]), 0, 0, 0, H, W, 1, 1,
+            check(lib.aether_gn_apply(ptr(x), ptr(out), N, C, G, ptr(mr), ptr(p["g"]), ptr(p["b"]), 0, 0, 0, 0, H, W, 1, 1,
                                       int(silu), current_stream()), "gn_apply")
             return out
         p = self._packed[name + ".norm_layer"]
         Tz, hz, wz, L = zq.shape
         z2 = zq.reshape(Tz * hz * wz, L)
-        py, pb = self._packed[name + ".conv_y"], self._packed[name + ".conv_b"]
-        zy = ops.gemm(z2, py["w"], py["b"], 0)          # 1x1x1 conv at latent resolution (commutes with nearest interp.)
-        zb = ops.gemm(z2, pb["w"], pb["b"], 0)
+        pyb = self._packed[name + ".conv_yb"]
+        zyb = ops.gemm(z2, pyb["w"], pyb["b"], 0)       # 1x1x1 convs at latent resolution (commute with nearest interp.)
+        zy, zb = zyb, zyb[:, C:]                        # column blocks [0, C) = conv_y, [C, 2C) = conv_b; row stride 2C
         if T > 1 and T % 2 == 1:
             tmap = [0] + [1 + ((t - 1) * (Tz - 1)) // (T - 1) for t in range(1, T)]
         else:
             tmap = [(t * Tz) // T for t in range(T)]
-        check(lib.aether_gn_apply(ptr(x), ptr(out), N, C, G, ptr(mr), ptr(p["g"]), ptr(p["b"]), ptr(zy), ptr(zb),
+        check(lib.aether_gn_apply(ptr(x), ptr(out), N, C, G, ptr(mr), ptr(p["g"]), ptr(p["b"]), ptr(zy), ptr(zb), 2 * C,
                                   ptr(self._imap(tmap)), H, W, hz, wz, int(silu), current_stream()), "gn_apply")
         return out
 

@@ -182,10 +182,11 @@ int64_t aether_gn_workspace_floats(int32_t C);
 int aether_gn_stats(const void* x, int64_t N, int32_t C, int32_t G, float eps, float* workspace, float* mean_rstd,
                     void* stream);
 /* y = SiLU?( GN(x) [* zy[map] + zb[map]] ): GroupNorm or CogVideoXSpatialNorm3D (zy/zb = conv_y/conv_b of the latent
- * at latent resolution [Tz, hz, wz, C]; tmap[t] = latent frame of frame t; rows/cols map by floor(y*hz/H)). */
+ * at latent resolution [Tz, hz, wz, .] with row stride zld elements (0 = C); tmap[t] = latent frame of frame t;
+ * rows/cols map by floor(y*hz/H)). */
 int aether_gn_apply(const void* x, void* y, int64_t N, int32_t C, int32_t G, const float* mean_rstd,
-                    const float* gamma, const float* beta, const void* zy, const void* zb, const int32_t* tmap,
-                    int32_t H, int32_t W, int32_t hz, int32_t wz, int32_t silu, void* stream);
+                    const float* gamma, const float* beta, const void* zy, const void* zb, int32_t zld,
+                    const int32_t* tmap, int32_t H, int32_t W, int32_t hz, int32_t wz, int32_t silu, void* stream);
 /* out[t', y', x', :] = in[tmap[t'], y'/sy, x'/sx, :]   (F.interpolate nearest; first-frame rule encoded in tmap) */
 int aether_upsample_nearest(const void* in, void* out, const int32_t* tmap, int32_t To, int32_t Ho, int32_t Wo,
                             int32_t Hi, int32_t Wi, int32_t sy, int32_t sx, int32_t C, void* stream);

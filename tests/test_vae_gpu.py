@@ -84,7 +84,7 @@ def test_groupnorm_silu(C, G):
     y = torch.empty_like(x)
     N = T * H * W
     check(lib.aether_gn_stats(ptr(x), N, C, G, 1e-6, ptr(ws), ptr(mr), current_stream()), "stats")
-    check(lib.aether_gn_apply(ptr(x), ptr(y), N, C, G, ptr(mr), ptr(gamma), ptr(beta), 0, 0, 0, H, W, 1, 1, 1,
+    check(lib.aether_gn_apply(ptr(x), ptr(y), N, C, G, ptr(mr), ptr(gamma), ptr(beta), 0, 0, 0, 0, H, W, 1, 1, 1,
                               current_stream()), "apply")
     xn = x.float().permute(3, 0, 1, 2)[None]
     ref = F.silu(F.group_norm(xn, G, gamma, beta, 1e-6))[0].permute(1, 2, 3, 0)

@@ -30,3 +30,39 @@ for it in range(2):
     print(f"decode: {t1 - t0:.3f} s  y {tuple(y.shape)} finite={bool(torch.isfinite(y.float()).all())} "
           f"std={y.float().std().item():.3f}", flush=True)
 print("mem GB", torch.cuda.max_memory_allocated() / 1e9)
+
+if "--breakdown" in sys.argv:
+    # CUDA-event time per kernel family (wrapping the module's own kernel-call helpers), one decode + one encode
+    import collections
+    rec = []
+
+    def wrap(name):
+        orig = getattr(vae, name)
+
+        def f(*a, **k):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            r = orig(*a, **k)
+            e.record()
+            tag = name
+            if name == "_conv":
+                p = vae._packed[a[1]]
+                tag = f"_conv k{p['k']} cin{p['cin']} cout{p['cout']}"
+            rec.append((tag, s, e))
+            return r
+        setattr(vae, name, f)
+
+    for n in ("_conv", "_norm", "_upsample", "_downsample", "_fill_time_pad", "_to_cl", "_blend"):
+        wrap(n)
+    for what, fn in (("decode", lambda: vae.decode(z)), ("encode", lambda: vae.encode(x).latent_dist.mode())):
+        rec.clear()
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        fn()
+        torch.cuda.synchronize(); wall = time.perf_counter() - t0
+        agg = collections.defaultdict(float); cnt = collections.Counter()
+        for tag, s, e in rec:
+            agg[tag] += s.elapsed_time(e); cnt[tag] += 1
+        print(f"--- {what}: wall {wall * 1e3:.0f} ms (nested helpers double count: _norm includes its GEMMs, "
+              f"_upsample/_downsample include their conv)")
+        for tag, ms in sorted(agg.items(), key=lambda kv: -kv[1])[:14]:
+            print(f"  {ms:8.1f} ms  x{cnt[tag]:5d}  {tag}")
