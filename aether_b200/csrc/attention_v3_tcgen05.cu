@@ -60,7 +60,7 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Params p
   uint64_t* o_full = p_free + 2;            // [2]
   uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(o_full + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform: uniform-datapath MMA issue
   const int lane = threadIdx.x & 31;
   const int q_blk = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int q0 = q_blk * 2 * BQ;
@@ -91,30 +91,42 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Params p
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_base_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_base_ptr, 0);
 
   if (warp < 4) {
     setmaxnreg_dec<48>();
-    if (warp == 0 && lane == 0) {
-      // ---------------------------------------------------------------- TMA producer
-      for (int t = 0; t < 2; ++t) {
-        mbar_arrive_expect_tx(&q_full[t], TILE_BYTES);
-        tma_load_4d(smem_q + t * TILE_BYTES, &tmap_qkv, &q_full[t], 0, h, q0 + t * BQ, b);
+    if (warp == 0) {
+      // ---------------------------------------------------------------- TMA producer (uniform control flow)
+      const bool lead = elect_one();
+      if (lead) {
+        for (int t = 0; t < 2; ++t) {
+          mbar_arrive_expect_tx(&q_full[t], TILE_BYTES);
+          tma_load_4d(smem_q + t * TILE_BYTES, &tmap_qkv, &q_full[t], 0, h, q0 + t * BQ, b);
+        }
       }
+      __syncwarp();
       int ks = 0, vs = 0;
       uint32_t kph = 0, vph = 0;
       for (int j = 0; j < n_kv; ++j) {
         mbar_wait(&k_empty[ks], kph ^ 1);
-        mbar_arrive_expect_tx(&k_full[ks], TILE_BYTES);
-        tma_load_4d(smem_k + ks * TILE_BYTES, &tmap_qkv, &k_full[ks], 0, H + h, j * BKV, b);
+        if (lead) {
+          mbar_arrive_expect_tx(&k_full[ks], TILE_BYTES);
+          tma_load_4d(smem_k + ks * TILE_BYTES, &tmap_qkv, &k_full[ks], 0, H + h, j * BKV, b);
+        }
+        __syncwarp();
         if (++ks == KSTAGES) { ks = 0; kph ^= 1; }
         mbar_wait(&v_empty[vs], vph ^ 1);
-        mbar_arrive_expect_tx(&v_full[vs], TILE_BYTES);
-        tma_load_4d(smem_v + vs * TILE_BYTES, &tmap_qkv, &v_full[vs], 0, 2 * H + h, j * BKV, b);
+        if (lead) {
+          mbar_arrive_expect_tx(&v_full[vs], TILE_BYTES);
+          tma_load_4d(smem_v + vs * TILE_BYTES, &tmap_qkv, &v_full[vs], 0, 2 * H + h, j * BKV, b);
+        }
+        __syncwarp();
         if (++vs == VSTAGES) { vs = 0; vph ^= 1; }
       }
-    } else if (warp == 1 && lane == 0) {
-      // ---------------------------------------------------------------- MMA issuer
+    } else if (warp == 1) {
+      // ---------------------------------------------------------------- MMA issuer: whole warp walks the schedule
+      // (uniform control flow -> plain UTCHMMA, no per-instruction ELECT waterfall); one elected lane issues.
+      const bool lead = elect_one();
       constexpr uint32_t idesc_qk = make_idesc_f16kind(BQ, BKV, 1, 1, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_f16kind(BQ, DH, 1, 1, 0, 1);
       const uint32_t s_col[2] = {tmem_base + COL_S0, tmem_base + COL_S1};
@@ -146,8 +158,11 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Params p
       mbar_wait(&k_full[0], 0);
       mbar_wait(&q_full[0], 0);
       tc_fence_after();
-      issue_qk(0, 0);
-      tc_commit(&s_full[0]);
+      if (lead) {
+        issue_qk(0, 0);
+        tc_commit(&s_full[0]);
+      }
+      __syncwarp();
       ks = 1;
       if (ks == KSTAGES) { ks = 0; kph ^= 1; }
       for (int j = 0; j < n_kv; ++j) {
@@ -158,47 +173,65 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Params p
           mbar_wait(&k_full[ks], kph);
           mbar_wait(&s_free[0], ph);
           tc_fence_after();
-          issue_qk(0, ks);
-          tc_commit(&s_full[0]);
+          if (lead) {
+            issue_qk(0, ks);
+            tc_commit(&s_full[0]);
+          }
+          __syncwarp();
         }
         if (j == 0) {
           mbar_wait(&q_full[1], 0);
           tc_fence_after();
-          issue_qk(1, 0);                      // K(0) is still resident: stage 0
-          tc_commit(&s_full[1]);
-          tc_commit(&k_empty[0]);
+          if (lead) {
+            issue_qk(1, 0);                    // K(0) is still resident: stage 0
+            tc_commit(&s_full[1]);
+            tc_commit(&k_empty[0]);
+          }
+          __syncwarp();
         } else {
           mbar_wait(&p_full[1], (j - 1) & 1);
           tc_fence_after();
-          issue_pv(1, vs1, j == 1);
-          tc_commit(&p_free[1]);
-          tc_commit(&v_empty[vs1]);
+          if (lead) {
+            issue_pv(1, vs1, j == 1);
+            tc_commit(&p_free[1]);
+            tc_commit(&v_empty[vs1]);
+          }
+          __syncwarp();
           if (++vs1 == VSTAGES) vs1 = 0;
         }
         // ---- phase B
         if (!last) {
           mbar_wait(&s_free[1], ph);
           tc_fence_after();
-          issue_qk(1, ks);
-          tc_commit(&s_full[1]);
-          tc_commit(&k_empty[ks]);
+          if (lead) {
+            issue_qk(1, ks);
+            tc_commit(&s_full[1]);
+            tc_commit(&k_empty[ks]);
+          }
+          __syncwarp();
           if (++ks == KSTAGES) { ks = 0; kph ^= 1; }
         }
         mbar_wait(&v_full[vs0], vph0);
         mbar_wait(&p_full[0], ph);
         tc_fence_after();
-        issue_pv(0, vs0, j == 0);
-        tc_commit(&p_free[0]);
-        if (last) tc_commit(&o_full[0]);
+        if (lead) {
+          issue_pv(0, vs0, j == 0);
+          tc_commit(&p_free[0]);
+          if (last) tc_commit(&o_full[0]);
+        }
+        __syncwarp();
         if (++vs0 == VSTAGES) { vs0 = 0; vph0 ^= 1; }
       }
       // drain: PV_1(n-1)
       mbar_wait(&p_full[1], (n_kv - 1) & 1);
       tc_fence_after();
-      issue_pv(1, vs1, n_kv == 1);
-      tc_commit(&p_free[1]);
-      tc_commit(&v_empty[vs1]);
-      tc_commit(&o_full[1]);
+      if (lead) {
+        issue_pv(1, vs1, n_kv == 1);
+        tc_commit(&p_free[1]);
+        tc_commit(&v_empty[vs1]);
+        tc_commit(&o_full[1]);
+      }
+      __syncwarp();
     }
   } else {
     // ------------------------------------------------------------------ softmax warpgroups

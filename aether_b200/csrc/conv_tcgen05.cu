@@ -70,7 +70,7 @@ conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform (see gemm_tcgen05.cu)
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.T * p.tiles_y * p.tiles_x * p.num_n;
   const int taps = p.kt * p.kh * p.kw;
@@ -94,10 +94,12 @@ conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_base_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_base_ptr, 0);
 
   if (warp == 0) {
-    if (lane == 0) {
+    // TMA producer: uniform control flow for the whole warp, one elected lane issues the copies
+    {
+      const bool lead = elect_one();
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -112,9 +114,12 @@ conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
               for (int cc = 0; cc < p.cin_chunks; ++cc, ++kb) {
                 mbar_wait(&empty[stage], phase ^ 1);
                 uint8_t* sa = smem + stage * C::STAGE_BYTES;
-                mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
-                tma_load_4d(sa, &tmap_x, &full[stage], cc * BK, x0 + dx, y0 + dy, t + dt);
-                tma_load_2d(sa + A_BYTES, &tmap_w, &full[stage], kb * BK, nb * BN);
+                if (lead) {
+                  mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
+                  tma_load_4d(sa, &tmap_x, &full[stage], cc * BK, x0 + dx, y0 + dy, t + dt);
+                  tma_load_2d(sa + A_BYTES, &tmap_w, &full[stage], kb * BK, nb * BN);
+                }
+                __syncwarp();
                 if (++stage == C::STAGES) {
                   stage = 0;
                   phase ^= 1;
@@ -123,7 +128,9 @@ conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // whole warp walks the schedule (uniform control flow -> back-to-back UTCHMMA); one elected lane issues
+    {
+      const bool lead = elect_one();
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -139,16 +146,20 @@ conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
           const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
           const uint64_t a_desc = make_sw128_desc(sa);
           const uint64_t b_desc = make_sw128_desc(sa + A_BYTES);
+          if (lead) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            tc_mma_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          tc_commit(&empty[stage]);
+            for (int k = 0; k < BK / 16; ++k)
+              tc_mma_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            tc_commit(&empty[stage]);
+          }
+          __syncwarp();
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        tc_commit(&tmem_full[acc]);
+        if (lead) tc_commit(&tmem_full[acc]);
+        __syncwarp();
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;

@@ -75,7 +75,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   uint64_t* tmem_empty = tmem_full + 2;     // [2]
   uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
-  const int warp = threadIdx.x >> 5;
+  // lane-0 broadcasts make warp index and TMEM base provably warp-uniform: role branches and MMA operands stay on
+  // the uniform datapath and ptxas emits back-to-back UTCHMMA instead of an ELECT / BRA.U.ANY waterfall per MMA.
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.num_m * p.num_n;
   const int num_kb = (p.K + BK - 1) / BK;
@@ -98,11 +100,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_base_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_base_ptr, 0);
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // ------------------------------------------------------------ TMA producer (uniform control flow, elected issue)
+    {
+      const bool lead = elect_one();
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -112,9 +115,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
-          mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
-          tma_load_2d(sa, &tmap_a, &full[stage], kb * BK, m_blk * BM);
-          tma_load_2d(sb, &tmap_b, &full[stage], kb * BK, n_blk * BN);
+          if (lead) {
+            mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
+            tma_load_2d(sa, &tmap_a, &full[stage], kb * BK, m_blk * BM);
+            tma_load_2d(sb, &tmap_b, &full[stage], kb * BK, n_blk * BN);
+          }
+          __syncwarp();
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -123,8 +129,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------ MMA issuer: the whole warp walks the tile / k-block
+    // schedule (uniform control flow, every lane polls the barriers); one elected lane issues MMAs and commits.
+    {
+      const bool lead = elect_one();
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -140,18 +148,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           const uint64_t a_desc = make_sw128_desc(sa);
           const uint64_t b_desc = make_sw128_desc(sa + A_BYTES);
+          if (lead) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // +32 bytes (encoded >>4 = 2) per K=16 step inside the 128B swizzle atom
-            tc_mma_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              // +32 bytes (encoded >>4 = 2) per K=16 step inside the 128B swizzle atom
+              tc_mma_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            }
+            tc_commit(&empty[stage]);
           }
-          tc_commit(&empty[stage]);
+          __syncwarp();
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        tc_commit(&tmem_full[acc]);
+        if (lead) tc_commit(&tmem_full[acc]);
+        __syncwarp();
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;

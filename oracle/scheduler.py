@@ -90,8 +90,13 @@ class OracleDPMScheduler:
             m3 = 1 + 1 / (2 * r)
             m4 = 1 / (2 * r)
         mn = (1 - a_prev) ** 0.5 * (1 - (-2 * h).exp()) ** 0.5
-        return dict(sqrt_a=a ** 0.5, sqrt_1ma=(1 - a) ** 0.5, m1=m1, m2=m2, m3=m3, m4=m4, m_noise=mn,
-                    prev_t=prev_t)
+        # The coefficients are 0-dim fp32 CPU tensors in diffusers.  On CUDA (where the reference runs) a
+        # `coef * bf16_tensor` product is computed in fp32 and rounded once; torch's CPU kernel instead rounds a
+        # 0-dim *first* operand to bf16 before multiplying.  Python floats take the fp32 path on both devices, so the
+        # oracle reproduces the CUDA semantics wherever it runs.
+        f = lambda v: None if v is None else float(v)  # noqa: E731
+        return dict(sqrt_a=f(a ** 0.5), sqrt_1ma=f((1 - a) ** 0.5), m1=f(m1), m2=f(m2), m3=f(m3), m4=f(m4),
+                    m_noise=f(mn), prev_t=prev_t)
 
     def step(self, model_output, old_pred_original_sample, timestep, timestep_back, sample,
              eta: float = 0.0, generator=None, return_dict: bool = False, noises=None):
