@@ -39,7 +39,10 @@ struct Params {
 //   is tracked on the side and applied to l immediately and to O at the start of the next tile (after PV_t(j) has
 //   retired).  If a tile ever exceeds the offset by more than 2^90 the tile is recomputed with its true maximum
 //   (S is still in TMEM), so no input can overflow.  The first tile establishes the offset with a max-only pass.
-template <bool PIPE>
+// POLY_MASK (modes 9-11): bit (i & 7) set => the i-th PAIR of exponentials of a row is evaluated by the FMA-pipe
+// polynomial exp2_poly_f32x2 instead of two MUFU.EX2 (ncu after the uniform-issue fix: MUFU 77 % busy, MIO-throttle
+// stalls, FMA pipe 20 %, issue slots 46 %: the MUFU is the binding pipe, so a fraction of its work moves over).
+template <bool PIPE, int POLY_MASK>
 __global__ void __launch_bounds__(THREADS, 1)
 attention_v3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -415,8 +418,15 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Params p
       uint32_t pk[64];
 #pragma unroll
       for (int c = 0; c < 128; c += 2) {
-        const float p0 = fast_exp2(fmaf(__uint_as_float(s[c]), sl2, neg_m));
-        const float p1 = fast_exp2(fmaf(__uint_as_float(s[c + 1]), sl2, neg_m));
+        const float x0 = fmaf(__uint_as_float(s[c]), sl2, neg_m);
+        const float x1 = fmaf(__uint_as_float(s[c + 1]), sl2, neg_m);
+        float p0, p1;
+        if ((POLY_MASK >> ((c >> 1) & 7)) & 1) {
+          exp2_poly_f32x2(x0, x1, p0, p1);
+        } else {
+          p0 = fast_exp2(x0);
+          p1 = fast_exp2(x1);
+        }
         sum[c & 7] += p0;
         sum[(c + 1) & 7] += p1;
         pk[c >> 1] = pack_bf16x2(p0, p1);
@@ -478,25 +488,26 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Params p
 
 }  // namespace attn3
 
-int attention_v3_launch(const CUtensorMap& tm, int B, int S, int H, void* out, float scale_log2, int pipelined,
+int attention_v3_launch(const CUtensorMap& tm, int B, int S, int H, void* out, float scale_log2, int variant,
                         cudaStream_t stream) {
+  // variant: 0 = mode 5, 1 = mode 6 (pipelined softmax), 2/3/4 = mode 5 with 25 % / 12.5 % / 37.5 % polynomial exp2
+  using Kernel = void (*)(const CUtensorMap, const attn3::Params);
+  static const Kernel kernels[5] = {attn3::attention_v3_kernel<false, 0>, attn3::attention_v3_kernel<true, 0>,
+                                    attn3::attention_v3_kernel<false, 0x88>, attn3::attention_v3_kernel<false, 0x80>,
+                                    attn3::attention_v3_kernel<false, 0xA4>};
   static bool attr_set = false;
   if (!attr_set) {
-    AETHER_CUDA_OK(cudaFuncSetAttribute(attn3::attention_v3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        attn3::SMEM_BYTES));
-    AETHER_CUDA_OK(cudaFuncSetAttribute(attn3::attention_v3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        attn3::SMEM_BYTES));
+    for (Kernel k : kernels)
+      AETHER_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, attn3::SMEM_BYTES));
     attr_set = true;
   }
+  AETHER_CHECK_ARG(variant >= 0 && variant < 5);
   attn3::Params p;
   p.B = B; p.H = H; p.S = S;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.scale_log2 = scale_log2;
   dim3 grid((unsigned)ceil_div(S, 2 * attn3::BQ), (unsigned)H, (unsigned)B);
-  if (pipelined)
-    attn3::attention_v3_kernel<true><<<grid, attn3::THREADS, attn3::SMEM_BYTES, stream>>>(tm, p);
-  else
-    attn3::attention_v3_kernel<false><<<grid, attn3::THREADS, attn3::SMEM_BYTES, stream>>>(tm, p);
+  kernels[variant]<<<grid, attn3::THREADS, attn3::SMEM_BYTES, stream>>>(tm, p);
   AETHER_CUDA_OK(cudaGetLastError());
   return AETHER_OK;
 }

@@ -44,7 +44,7 @@ attention_v4_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Params p
   uint64_t* o_full = p_free + 1;
   uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(o_full + 1);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform (see gemm_tcgen05.cu)
   const int lane = threadIdx.x & 31;
   const int q_blk = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int q0 = q_blk * BQ;
@@ -73,27 +73,40 @@ attention_v4_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Params p
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_base_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_base_ptr, 0);
 
   if (warp == 0) {
-    if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, TILE_BYTES);
-      tma_load_4d(smem_q, &tmap_qkv, q_full, 0, h, q0, b);
+    setmaxnreg_dec<48>();
+    {
+      const bool lead = elect_one();
+      if (lead) {
+        mbar_arrive_expect_tx(q_full, TILE_BYTES);
+        tma_load_4d(smem_q, &tmap_qkv, q_full, 0, h, q0, b);
+      }
+      __syncwarp();
       int ks = 0, vs = 0;
       uint32_t kph = 0, vph = 0;
       for (int j = 0; j < n_kv; ++j) {
         mbar_wait(&k_empty[ks], kph ^ 1);
-        mbar_arrive_expect_tx(&k_full[ks], TILE_BYTES);
-        tma_load_4d(smem_k + ks * TILE_BYTES, &tmap_qkv, &k_full[ks], 0, H + h, j * BKV, b);
+        if (lead) {
+          mbar_arrive_expect_tx(&k_full[ks], TILE_BYTES);
+          tma_load_4d(smem_k + ks * TILE_BYTES, &tmap_qkv, &k_full[ks], 0, H + h, j * BKV, b);
+        }
+        __syncwarp();
         if (++ks == KSTAGES) { ks = 0; kph ^= 1; }
         mbar_wait(&v_empty[vs], vph ^ 1);
-        mbar_arrive_expect_tx(&v_full[vs], TILE_BYTES);
-        tma_load_4d(smem_v + vs * TILE_BYTES, &tmap_qkv, &v_full[vs], 0, 2 * H + h, j * BKV, b);
+        if (lead) {
+          mbar_arrive_expect_tx(&v_full[vs], TILE_BYTES);
+          tma_load_4d(smem_v + vs * TILE_BYTES, &tmap_qkv, &v_full[vs], 0, 2 * H + h, j * BKV, b);
+        }
+        __syncwarp();
         if (++vs == VSTAGES) { vs = 0; vph ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    setmaxnreg_dec<48>();
+    {
+      const bool lead = elect_one();   // whole warp walks the schedule (uniform control flow), one lane issues
       constexpr uint32_t idesc_qk = make_idesc_f16kind(BQ, BKV, 1, 1, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_f16kind(BQ, DH, 1, 1, 0, 1);
       const uint32_t s_col = tmem_base + COL_S, p_col = tmem_base + COL_P, o_col = tmem_base + COL_O;
@@ -108,9 +121,12 @@ attention_v4_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Params p
       mbar_wait(&k_full[0], 0);
       mbar_wait(q_full, 0);
       tc_fence_after();
-      issue_qk(0);
-      tc_commit(s_full);
-      tc_commit(&k_empty[0]);
+      if (lead) {
+        issue_qk(0);
+        tc_commit(s_full);
+        tc_commit(&k_empty[0]);
+      }
+      __syncwarp();
       ks = 1;
       if (ks == KSTAGES) { ks = 0; kph ^= 1; }
       for (int j = 0; j < n_kv; ++j) {
@@ -119,27 +135,32 @@ attention_v4_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Params p
           mbar_wait(&k_full[ks], kph);
           mbar_wait(s_free, j & 1);
           tc_fence_after();
-          issue_qk(ks);
-          tc_commit(s_full);
-          tc_commit(&k_empty[ks]);
+          if (lead) {
+            issue_qk(ks);
+            tc_commit(s_full);
+            tc_commit(&k_empty[ks]);
+          }
+          __syncwarp();
           if (++ks == KSTAGES) { ks = 0; kph ^= 1; }
         }
         mbar_wait(&v_full[vs], vph);
         mbar_wait(p_full, j & 1);
         tc_fence_after();
-        {
+        if (lead) {
           const uint64_t v_desc = make_sw128_desc(smem_u32(smem_v + vs * TILE_BYTES));
 #pragma unroll
           for (int k = 0; k < BKV / 16; ++k)
             tc_mma_ts(o_col, p_col + 8 * k, v_desc + 128 * k, idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+          tc_commit(p_free);
+          tc_commit(&v_empty[vs]);
+          if (last) tc_commit(o_full);
         }
-        tc_commit(p_free);
-        tc_commit(&v_empty[vs]);
-        if (last) tc_commit(o_full);
+        __syncwarp();
         if (++vs == VSTAGES) { vs = 0; vph ^= 1; }
       }
     }
   } else {
+    setmaxnreg_inc<224>();   // 4 x 224 + 2 x 48 registers per lane fit the 192 x 168 the CTA is launched with
     const int q = warp & 3;
     const int row_in_tile = q * 32 + lane;
     const uint32_t lane_off = uint32_t(q * 32) << 16;

@@ -303,6 +303,22 @@ __device__ __forceinline__ uint32_t exp2_poly_f16x2_from_f32x2(uint64_t x) {
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(r1), "f"(r0));
   return h;
 }
+// Same range reduction and cubic, fp32 results (for the bf16-P attention kernels): 2 FMNMX + 7 packed FMA-pipe ops +
+// 2 integer ops per PAIR of exponentials instead of 2 MUFU.EX2 (the MUFU is the binding pipe at head_dim 64).
+__device__ __forceinline__ void exp2_poly_f32x2(float x0, float x1, float& r0, float& r1) {
+  const uint64_t xc = pack_f32x2(fmaxf(x0, -126.f), fmaxf(x1, -126.f));
+  const uint64_t t = fadd2(xc, pack_f32x2(12582912.f, 12582912.f));
+  const uint64_t jf = fadd2(t, pack_f32x2(-12582912.f, -12582912.f));
+  const uint64_t f = ffma2(jf, pack_f32x2(-1.f, -1.f), xc);
+  uint64_t pl = ffma2(f, pack_f32x2(0.055171460f, 0.055171460f), pack_f32x2(0.24261086f, 0.24261086f));
+  pl = ffma2(pl, f, pack_f32x2(0.69326097f, 0.69326097f));
+  pl = ffma2(pl, f, pack_f32x2(0.99992812f, 0.99992812f));
+  float p0, p1, t0, t1;
+  unpack_f32x2(pl, p0, p1);
+  unpack_f32x2(t, t0, t1);
+  r0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(t0) << 23));
+  r1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
+}
 // exp2 of two fp32 values given as a packed pair, computed as ONE half-precision MUFU op:
 // cvt.rn.f16x2.f32 (hi -> upper half, lo -> lower half) then ex2.approx.f16x2.  Result: packed f16x2 (lo in [15:0]).
 __device__ __forceinline__ uint32_t exp2_f16x2_from_f32x2(uint64_t x) {
