@@ -447,6 +447,7 @@ int attention_v3_launch(const CUtensorMap& tm, int B, int S, int H, void* out, f
                         cudaStream_t stream);
 int attention_v4_launch(const CUtensorMap& tm, int B, int S, int H, void* out, float scale_log2, cudaStream_t stream);
 int attention_v5_launch(const void* qkv, int B, int S, int H, void* out, float scale_log2, cudaStream_t stream);
+int attention_v6_launch(const void* qkv, int B, int S, int H, void* out, float scale_log2, cudaStream_t stream);
 
 // v_fp16 != 0: the V third of qkv holds fp16 values (GEMM f16_from_col) and an fp16-P mode runs:
 //   1 = every exponential on the MUFU, 2 = 40 % of them as an FMA-pipe polynomial (the product default).
@@ -476,6 +477,7 @@ int attention_bf16(const void* qkv, void* out, int B, int S, int H, float softma
     case 9: return attention_v3_launch(tm, B, S, H, out, p.scale_log2, 2, stream);   // mode 5 + 25 % polynomial exp2
     case 10: return attention_v3_launch(tm, B, S, H, out, p.scale_log2, 3, stream);  // 12.5 %
     case 11: return attention_v3_launch(tm, B, S, H, out, p.scale_log2, 4, stream);  // 37.5 %
+    case 12: return attention_v6_launch(qkv, B, S, H, out, p.scale_log2, stream);    // 3 query tiles, 12 softmax warps
     case 8: return attention_v5_launch(qkv, B, S, H, out, p.scale_log2, stream);     // 64-key tiles, S load in flight
     default: return attn::launch<3>(tm, p, grid, stream);   // 3: bf16 V, chunked softmax (v_fp16 is a mode id)
   }

@@ -76,7 +76,6 @@ attention_v4_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Params p
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_base_ptr, 0);
 
   if (warp == 0) {
-    setmaxnreg_dec<48>();
     {
       const bool lead = elect_one();
       if (lead) {
@@ -104,7 +103,6 @@ attention_v4_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Params p
       }
     }
   } else if (warp == 1) {
-    setmaxnreg_dec<48>();
     {
       const bool lead = elect_one();   // whole warp walks the schedule (uniform control flow), one lane issues
       constexpr uint32_t idesc_qk = make_idesc_f16kind(BQ, BKV, 1, 1, 0, 0);
@@ -160,7 +158,7 @@ attention_v4_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Params p
       }
     }
   } else {
-    setmaxnreg_inc<224>();   // 4 x 224 + 2 x 48 registers per lane fit the 192 x 168 the CTA is launched with
+    // (no setmaxnreg here: with 6 warps the second warpgroup is incomplete and the .sync.aligned rebalance hangs)
     const int q = warp & 3;
     const int row_in_tile = q * 32 + lane;
     const uint32_t lane_off = uint32_t(q * 32) << 16;

@@ -128,10 +128,11 @@ class AetherTransformer3D(nn.Module):
         self._packed = None
         self._ws = None
         self._n_layers_override = -1
-        # kernel-mode switch (not a model hyper-parameter): fp16 P/V attention with ex2.f16x2 (default) or the
-        # bf16 P/V variant; set before pack().
-        self.attention_fp16_pv = 5     # attention kernel mode 0..5 (csrc/attention*_tcgen05.cu); 5 = decoupled S/P
-        #                                buffers + skewed MMA schedule, measured fastest (3.76 ms vs 4.03 ms for mode 0)
+        # kernel-mode switch (not a model hyper-parameter), set before pack(): attention kernel variant 0..12
+        # (csrc/attention*_tcgen05.cu, DESIGN.md "Attention roofline"); 5 = decoupled S/P buffers + skewed MMA
+        # schedule, measured fastest (3.30 ms at S=15076).  AETHER_ATTENTION_MODE overrides it for A/B timing.
+        import os
+        self.attention_fp16_pv = int(os.environ.get("AETHER_ATTENTION_MODE", "5"))
 
     # ------------------------------------------------------------------ torch plumbing
     @property
