@@ -61,6 +61,91 @@ __device__ __forceinline__ float gelu_tanh(float x) {
   return 0.5f * x * (1.0f + t);
 }
 
+// Epilogue of one 128 x 256 accumulator tile, executed by the 128 epilogue threads of a CTA (thread = row):
+// tcgen05.ld 64-column chunks, bias / GELU-tanh / gate*x + residual, pack, swizzled smem staging, TMA store.
+// `taddr_tile` = TMEM address of the tile's column 0 in this warp's lane quarter.  Shared by the 1-CTA and 2-CTA kernels.
+template <int EPI>
+__device__ __forceinline__ void epilogue_tile(const Params& p, const CUtensorMap* tmap_c, uint32_t taddr_tile, int m_blk,
+                                              int n_blk, int row_in_tile, uint8_t* smem_c, int& cbuf,
+                                              bool store_leader) {
+  const int row = m_blk * BM + row_in_tile;
+  const bool row_ok = row < p.M;
+  const float* gate = nullptr;
+  if (EPI == 2) {
+    const int b = row_ok ? row / p.S : 0;
+    const int s = row_ok ? row - b * p.S : 0;
+    gate = (s < p.St ? p.gate_txt : p.gate_vid) + b * p.gate_bstride;
+  }
+#pragma unroll 1
+  for (int ch = 0; ch < BN / CCHUNK; ++ch) {
+    const int n0 = n_blk * BN + ch * CCHUNK;
+    if (n0 >= p.N) break;
+    uint32_t v0[32], v1[32];
+    const uint32_t taddr = taddr_tile + ch * CCHUNK;
+    tmem_ld_32x32b_x32(taddr, v0);
+    tmem_ld_32x32b_x32(taddr + 32, v1);
+    tc_wait_ld();
+
+    uint32_t packed[32];
+#pragma unroll
+    for (int g8 = 0; g8 < 8; ++g8) {     // 8 groups of 8 columns (one 16-byte bf16 vector each)
+      float x[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = g8 * 8 + j;
+        x[j] = __uint_as_float(c < 32 ? v0[c] : v1[c - 32]);
+      }
+      const int n = n0 + g8 * 8;
+      const bool col_ok = n < p.N;       // N % 8 == 0 is required
+      if (p.bias != nullptr && col_ok) {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
+        x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
+        x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+      }
+      if (EPI == 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = gelu_tanh(x[j]);
+      }
+      if (EPI == 2) {
+        if (row_ok && col_ok) {
+          const float4 g0 = __ldg(reinterpret_cast<const float4*>(gate + n));
+          const float4 g1 = __ldg(reinterpret_cast<const float4*>(gate + n + 4));
+          const uint4 r = *reinterpret_cast<const uint4*>(p.C + int64_t(row) * p.ldc + n);
+          x[0] = bf16_lo(r.x) + g0.x * x[0]; x[1] = bf16_hi(r.x) + g0.y * x[1];
+          x[2] = bf16_lo(r.y) + g0.z * x[2]; x[3] = bf16_hi(r.y) + g0.w * x[3];
+          x[4] = bf16_lo(r.z) + g1.x * x[4]; x[5] = bf16_hi(r.z) + g1.y * x[5];
+          x[6] = bf16_lo(r.w) + g1.z * x[6]; x[7] = bf16_hi(r.w) + g1.w * x[7];
+        }
+      }
+      if (n >= p.f16_from) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) packed[g8 * 4 + j] = pack_f16x2(x[2 * j], x[2 * j + 1]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) packed[g8 * 4 + j] = pack_bf16x2(x[2 * j], x[2 * j + 1]);
+      }
+    }
+    // staging buffer `cbuf` was last used two chunks ago; make sure that TMA store has read it
+    if (store_leader) tma_store_wait_read<1>();
+    named_bar_sync(1, 128);
+    uint8_t* crow = smem_c + cbuf * C_BYTES + row_in_tile * 128;
+#pragma unroll
+    for (int c16 = 0; c16 < 8; ++c16) {
+      const int phys = c16 ^ (row_in_tile & 7);
+      *reinterpret_cast<uint4*>(crow + phys * 16) =
+          make_uint4(packed[c16 * 4], packed[c16 * 4 + 1], packed[c16 * 4 + 2], packed[c16 * 4 + 3]);
+    }
+    fence_proxy_async_smem();
+    named_bar_sync(1, 128);
+    if (store_leader) {
+      tma_store_2d(tmap_c, smem_c + cbuf * C_BYTES, n0, m_blk * BM);
+      tma_store_commit();
+    }
+    cbuf ^= 1;
+  }
+}
+
 template <int EPI>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -181,84 +266,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       int m_blk, n_blk;
       tile_coords(t, p, m_blk, n_blk);
-      const int row = m_blk * BM + row_in_tile;
-      const bool row_ok = row < p.M;
-      const float* gate = nullptr;
-      if (EPI == 2) {
-        const int b = row_ok ? row / p.S : 0;
-        const int s = row_ok ? row - b * p.S : 0;
-        gate = (s < p.St ? p.gate_txt : p.gate_vid) + b * p.gate_bstride;
-      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-#pragma unroll 1
-      for (int ch = 0; ch < BN / CCHUNK; ++ch) {
-        const int n0 = n_blk * BN + ch * CCHUNK;
-        if (n0 >= p.N) break;
-        uint32_t v0[32], v1[32];
-        const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * BN + ch * CCHUNK;
-        tmem_ld_32x32b_x32(taddr, v0);
-        tmem_ld_32x32b_x32(taddr + 32, v1);
-        tc_wait_ld();
-
-        uint32_t packed[32];
-#pragma unroll
-        for (int g8 = 0; g8 < 8; ++g8) {     // 8 groups of 8 columns (one 16-byte bf16 vector each)
-          float x[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int c = g8 * 8 + j;
-            x[j] = __uint_as_float(c < 32 ? v0[c] : v1[c - 32]);
-          }
-          const int n = n0 + g8 * 8;
-          const bool col_ok = n < p.N;       // N % 8 == 0 is required
-          if (p.bias != nullptr && col_ok) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
-            x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
-            x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
-          }
-          if (EPI == 1) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) x[j] = gelu_tanh(x[j]);
-          }
-          if (EPI == 2) {
-            if (row_ok && col_ok) {
-              const float4 g0 = __ldg(reinterpret_cast<const float4*>(gate + n));
-              const float4 g1 = __ldg(reinterpret_cast<const float4*>(gate + n + 4));
-              const uint4 r = *reinterpret_cast<const uint4*>(p.C + int64_t(row) * p.ldc + n);
-              x[0] = bf16_lo(r.x) + g0.x * x[0]; x[1] = bf16_hi(r.x) + g0.y * x[1];
-              x[2] = bf16_lo(r.y) + g0.z * x[2]; x[3] = bf16_hi(r.y) + g0.w * x[3];
-              x[4] = bf16_lo(r.z) + g1.x * x[4]; x[5] = bf16_hi(r.z) + g1.y * x[5];
-              x[6] = bf16_lo(r.w) + g1.z * x[6]; x[7] = bf16_hi(r.w) + g1.w * x[7];
-            }
-          }
-          if (n >= p.f16_from) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) packed[g8 * 4 + j] = pack_f16x2(x[2 * j], x[2 * j + 1]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) packed[g8 * 4 + j] = pack_bf16x2(x[2 * j], x[2 * j + 1]);
-          }
-        }
-        // staging buffer `cbuf` was last used two chunks ago; make sure that TMA store has read it
-        if (store_leader) tma_store_wait_read<1>();
-        named_bar_sync(1, 128);
-        uint8_t* crow = smem_c + cbuf * C_BYTES + row_in_tile * 128;
-#pragma unroll
-        for (int c16 = 0; c16 < 8; ++c16) {
-          const int phys = c16 ^ (row_in_tile & 7);
-          *reinterpret_cast<uint4*>(crow + phys * 16) =
-              make_uint4(packed[c16 * 4], packed[c16 * 4 + 1], packed[c16 * 4 + 2], packed[c16 * 4 + 3]);
-        }
-        fence_proxy_async_smem();
-        named_bar_sync(1, 128);
-        if (store_leader) {
-          tma_store_2d(&tmap_c, smem_c + cbuf * C_BYTES, n0, m_blk * BM);
-          tma_store_commit();
-        }
-        cbuf ^= 1;
-      }
+      epilogue_tile<EPI>(p, &tmap_c, tmem_base + (uint32_t(q * 32) << 16) + acc * BN, m_blk, n_blk, row_in_tile, smem_c,
+                         cbuf, store_leader);
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) {
@@ -275,6 +286,174 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2): a cluster of two CTAs on one TPC owns a 256 x 256 output tile.  CTA r loads
+// its own 128 rows of A and HALF of the W tile (128 of the 256 output columns); the leader issues
+// tcgen05.mma.cta_group::2 (M = 256, N = 256, K = 16) which feeds both tensor cores from both halves.  Per SM and
+// k-block the shared-memory traffic drops from 48 KB written + 48 KB read to 32 + 32 KB -- with one CTA per SM that
+// traffic (192 B/clk against the 128 B/clk/SM the tensor core itself needs) was the reason the 1-CTA kernel stalls
+// at ~81 % tensor-pipe activity -- and the stage shrinks to 32 KB, so the ring holds 6 stages instead of 4.
+//   full[s]       leader's barrier: 1 arrive.expect_tx (leader producer) + 64 KB of complete_tx from BOTH CTAs' TMA
+//   empty[s]      per CTA, armed by the leader's multicast tcgen05.commit (the pair's MMAs have read both stages)
+//   tmem_full[a]  per CTA, multicast commit;   tmem_empty[a]  leader's, 256 arrivals (both CTAs' epilogue threads)
+constexpr int STAGES2 = 6;
+constexpr int BH_BYTES = (BN / 2) * BK * 2;          // half of the W tile
+constexpr int STAGE2_BYTES = A_BYTES + BH_BYTES;     // 32 KB
+constexpr int SMEM2_BYTES = 1024 + STAGES2 * STAGE2_BYTES + 2 * C_BYTES + 256;
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_bh,
+             const __grid_constant__ CUtensorMap tmap_c, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_c = smem + STAGES2 * STAGE2_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + 2 * C_BYTES);
+  uint64_t* full = bars;                     // [STAGES2]  (used in the leader)
+  uint64_t* empty = bars + STAGES2;          // [STAGES2]
+  uint64_t* tmem_full = bars + 2 * STAGES2;  // [2]
+  uint64_t* tmem_empty = tmem_full + 2;      // [2]        (used in the leader)
+  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();               // 0 = leader
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int num_tiles = p.num_m * p.num_n;               // num_m counts 256-row pair tiles here
+  const int num_kb = (p.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_bh);
+    tma_prefetch_desc(&tmap_c);
+    for (int i = 0; i < STAGES2; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 256);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc_2cta<512>(tmem_base_ptr);
+  tc_fence_before();
+  cluster_sync_all();                                    // barriers of BOTH CTAs initialised before any remote signal
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_base_ptr, 0);
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (both CTAs)
+    const bool lead = elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = pair; t < num_tiles; t += num_pairs) {
+      int m2, n_blk;
+      tile_coords(t, p, m2, n_blk);
+      const int m_row = (2 * m2 + int(rank)) * BM;
+      const int n_row = n_blk * BN + int(rank) * (BN / 2);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * STAGE2_BYTES;
+        if (lead) {
+          if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * STAGE2_BYTES);
+          tma_load_2d_2cta(sa, &tmap_a, &full[stage], kb * BK, m_row);
+          tma_load_2d_2cta(sa + A_BYTES, &tmap_bh, &full[stage], kb * BK, n_row);
+        }
+        __syncwarp();
+        if (++stage == STAGES2) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (rank == 0) {
+      const bool lead = elect_one();
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = pair; t < num_tiles; t += num_pairs) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE2_BYTES);
+          const uint64_t a_desc = make_sw128_desc(sa);
+          const uint64_t b_desc = make_sw128_desc(sa + A_BYTES);
+          if (lead) {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              tc_mma_ss_2cta(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            tc_commit_2cta(&empty[stage], 3);
+          }
+          __syncwarp();
+          if (++stage == STAGES2) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        if (lead) tc_commit_2cta(&tmem_full[acc], 3);
+        __syncwarp();
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..5 of each CTA, own 128 rows)
+    const int q = warp & 3;
+    const int row_in_tile = q * 32 + lane;
+    const bool store_leader = (threadIdx.x == 64);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int cbuf = 0;
+    for (int t = pair; t < num_tiles; t += num_pairs) {
+      int m2, n_blk;
+      tile_coords(t, p, m2, n_blk);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      epilogue_tile<EPI>(p, &tmap_c, tmem_base + (uint32_t(q * 32) << 16) + acc * BN, 2 * m2 + int(rank), n_blk,
+                         row_in_tile, smem_c, cbuf, store_leader);
+      tc_fence_before();
+      mbar_arrive_cluster(&tmem_empty[acc], 0);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+    if (store_leader) tma_store_wait<0>();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();                                    // the pair's MMAs and remote arrivals are done in both CTAs
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2cta<512>(tmem_base);
+  }
+}
+
+template <int EPI>
+int launch2(const CUtensorMap& ta, const CUtensorMap& tbh, const CUtensorMap& tc, const Params& p, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    AETHER_CUDA_OK(cudaFuncSetAttribute(gemm2_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+    attr_set = true;
+  }
+  const int tiles = p.num_m * p.num_n;
+  const int pairs = num_sms() / 2;
+  const int grid = 2 * (tiles < pairs ? tiles : pairs);
+  gemm2_kernel<EPI><<<grid, THREADS, SMEM2_BYTES, stream>>>(ta, tbh, tc, p);
+  AETHER_CUDA_OK(cudaGetLastError());
+  return AETHER_OK;
 }
 
 template <int EPI>
@@ -317,6 +496,22 @@ int gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, i
   p.C = reinterpret_cast<__nv_bfloat16*>(C);
   p.ldc = ldc;
   p.f16_from = f16_from_col < 0 ? 0x7fffffff : f16_from_col;
+  // Large problems run on CTA pairs (cta_group::2); AETHER_GEMM_1CTA=1 forces the single-CTA kernel for A/B timing.
+  static const bool force_1cta = [] {
+    const char* e = getenv("AETHER_GEMM_1CTA");
+    return e != nullptr && e[0] == '1';
+  }();
+  if (!force_1cta && M >= 1024 && N >= gemm::BN && num_sms() >= 2) {
+    CUtensorMap tbh;
+    if ((rc = make_tmap_2d(&tbh, W, N, K, ldw, gemm::BN / 2, gemm::BK))) return rc;
+    gemm::Params p2 = p;
+    p2.num_m = (int)ceil_div(M, 2 * gemm::BM);
+    switch (epilogue) {
+      case 0: return gemm::launch2<0>(ta, tbh, tc, p2, stream);
+      case 1: return gemm::launch2<1>(ta, tbh, tc, p2, stream);
+      default: return gemm::launch2<2>(ta, tbh, tc, p2, stream);
+    }
+  }
   switch (epilogue) {
     case 0: return gemm::launch<0>(ta, tb, tc, p, stream);
     case 1: return gemm::launch<1>(ta, tb, tc, p, stream);

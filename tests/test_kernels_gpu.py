@@ -44,6 +44,45 @@ def test_gemm_bias(M, N, K):
     _close(out, ref, 2 ** -7, 2e-2, f"gemm {M}x{N}x{K}")
 
 
+@pytest.mark.parametrize("M,N,K,epi", [(1025, 256, 128, 0), (1400, 320, 192, 0), (2048, 512, 64, 1), (3000, 768, 320, 1),
+                                       (15076, 256, 256, 0)])
+def test_gemm_cta_pair(M, N, K, epi):
+    """M >= 1024 runs the cta_group::2 kernel: ragged M (second CTA of the last pair partly / fully out of range),
+    ragged N (W rows zero-filled by TMA), fewer tiles than CTA pairs, both arithmetic epilogues."""
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(M + N + K)
+    a = torch.randn(M, K, device=DEV, generator=g).bfloat16()
+    w = (torch.randn(N, K, device=DEV, generator=g) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device=DEV, generator=g) * 0.5
+    out = ops.gemm(a, w, bias, epi)
+    ref = a.float() @ w.float().t() + bias
+    if epi == 1:
+        ref = torch.nn.functional.gelu(ref, approximate="tanh")
+    _close(out, ref, 2 ** -7, 2e-2, f"gemm2 {M}x{N}x{K} epi{epi}")
+
+
+def test_gemm_cta_pair_gated_residual_fp16_columns():
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(66)
+    B, S, St, N, K = 2, 1283, 226, 512, 256
+    M = B * S
+    a = torch.randn(M, K, device=DEV, generator=g).bfloat16()
+    w = (torch.randn(N, K, device=DEV, generator=g) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device=DEV, generator=g) * 0.1
+    gate_v = torch.randn(B, N, device=DEV, generator=g)
+    gate_t = torch.randn(B, N, device=DEV, generator=g)
+    resid = torch.randn(M, N, device=DEV, generator=g).bfloat16()
+    out = resid.clone()
+    ops.gemm(a, w, bias, 2, out=out, gate_vid=gate_v, gate_txt=gate_t, S=S, St=St)
+    y = (a.float() @ w.float().t() + bias).view(B, S, N)
+    gate = torch.where((torch.arange(S, device=DEV) < St)[None, :, None], gate_t[:, None, :], gate_v[:, None, :])
+    _close(out.view(B, S, N), resid.float().view(B, S, N) + gate * y, 2 ** -7, 3e-2, "gemm2 gated residual")
+    out16 = ops.gemm(a, w, bias, 0, f16_from_col=256)
+    ref = a.float() @ w.float().t() + bias
+    _close(out16[:, :256], ref[:, :256], 2 ** -7, 2e-2, "gemm2 bf16 part")
+    _close(out16.view(torch.float16)[:, 256:], ref[:, 256:], 2 ** -10, 2e-3, "gemm2 fp16 part")
+
+
 def test_gemm_gelu():
     ops = _ops()
     g = torch.Generator(device=DEV).manual_seed(5)
