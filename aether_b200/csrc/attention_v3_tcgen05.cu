@@ -416,12 +416,28 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Params p
 #pragma unroll
       for (int c = 0; c < 8; ++c) sum[c] = 0.f;
       uint32_t pk[64];
+      // ORDERED (POLY_MASK < 0, mode 13): ptxas hoists the MUFU.EX2 of the whole tile ahead of the row-sum adds and
+      // bf16 packs, so each warp ends its tile with ~150 issue slots of FADD / F2FP and no MUFU work, and the warps of
+      // a scheduler -- which run in lock-step -- leave the XU idle together.  A run-time zero derived from the partial
+      // sums of chunk k-2 is added to the exponent offset of chunk k: a true data dependency (x * 0 is not foldable
+      // under IEEE rules) that keeps at most two 16-column chunks of exponentials in flight and so interleaves the
+      // consumers with the MUFU stream.
+      float zero_dep[2] = {0.f, 0.f};
 #pragma unroll
       for (int c = 0; c < 128; c += 2) {
-        const float x0 = fmaf(__uint_as_float(s[c]), sl2, neg_m);
-        const float x1 = fmaf(__uint_as_float(s[c + 1]), sl2, neg_m);
+        float off = neg_m;
+        if (POLY_MASK < 0) {
+          const int chunk = c >> 4;
+          if ((c & 15) == 0) {                      // snapshot of the sums of chunks < chunk, consumed by chunk + 1
+            const float partial = ((sum[0] + sum[1]) + (sum[2] + sum[3])) + ((sum[4] + sum[5]) + (sum[6] + sum[7]));
+            zero_dep[chunk & 1] = 0.f * partial;
+          }
+          off = neg_m + zero_dep[(chunk + 1) & 1];  // written at the start of chunk - 1: depends on chunks <= chunk - 2
+        }
+        const float x0 = fmaf(__uint_as_float(s[c]), sl2, off);
+        const float x1 = fmaf(__uint_as_float(s[c + 1]), sl2, off);
         float p0, p1;
-        if ((POLY_MASK >> ((c >> 1) & 7)) & 1) {
+        if (POLY_MASK > 0 && ((POLY_MASK >> ((c >> 1) & 7)) & 1)) {
           exp2_poly_f32x2(x0, x1, p0, p1);
         } else {
           p0 = fast_exp2(x0);
@@ -492,16 +508,16 @@ int attention_v3_launch(const CUtensorMap& tm, int B, int S, int H, void* out, f
                         cudaStream_t stream) {
   // variant: 0 = mode 5, 1 = mode 6 (pipelined softmax), 2/3/4 = mode 5 with 25 % / 12.5 % / 37.5 % polynomial exp2
   using Kernel = void (*)(const CUtensorMap, const attn3::Params);
-  static const Kernel kernels[5] = {attn3::attention_v3_kernel<false, 0>, attn3::attention_v3_kernel<true, 0>,
+  static const Kernel kernels[6] = {attn3::attention_v3_kernel<false, 0>, attn3::attention_v3_kernel<true, 0>,
                                     attn3::attention_v3_kernel<false, 0x88>, attn3::attention_v3_kernel<false, 0x80>,
-                                    attn3::attention_v3_kernel<false, 0xA4>};
+                                    attn3::attention_v3_kernel<false, 0xA4>, attn3::attention_v3_kernel<false, -1>};
   static bool attr_set = false;
   if (!attr_set) {
     for (Kernel k : kernels)
       AETHER_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, attn3::SMEM_BYTES));
     attr_set = true;
   }
-  AETHER_CHECK_ARG(variant >= 0 && variant < 5);
+  AETHER_CHECK_ARG(variant >= 0 && variant < 6);
   attn3::Params p;
   p.B = B; p.H = H; p.S = S;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);

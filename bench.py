@@ -314,7 +314,8 @@ def run_product(args):
             "e2e": e2e,
             "gpu_launches": (model.launches_per_forward(1) + 1) * args.steps,
             "clocks": clocks,
-            "roofline": {"kernel": "attention_kernel (tcgen05)", "bound": "tensor", "achieved": achieved, "peak": peak,
+            "roofline": {"kernel": f"aether_attention_bf16 mode {int(model.attention_fp16_pv)} (tcgen05, attention_v3_kernel)",
+                         "bound": "tensor", "achieved": achieved, "peak": peak,
                          "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                          "peak_source": peak_src, "launches_timed": attn_n, "avg_launch_ms": avg_ms,
                          "share_of_step": attn_ms / (elapsed_ms / args.steps) if attn_n else None},
