@@ -480,8 +480,11 @@ int attention_bf16(const void* qkv, void* out, int B, int S, int H, float softma
     case 13: return attention_v3_launch(tm, B, S, H, out, p.scale_log2, 5, stream);  // mode 5, consumers interleaved
     case 12: return attention_v6_launch(qkv, B, S, H, out, p.scale_log2, stream);    // 3 query tiles, 12 softmax warps
     case 8: return attention_v5_launch(qkv, B, S, H, out, p.scale_log2, stream);     // 64-key tiles, S load in flight
-    default: return attn::launch<3>(tm, p, grid, stream);   // 3: bf16 V, chunked softmax (v_fp16 is a mode id)
+    case 3: return attn::launch<3>(tm, p, grid, stream);    // bf16 V, chunked two-pass softmax
+    default: break;
   }
+  AETHER_CHECK_ARG(!"unknown attention variant id (v_fp16 must be 0..13)");
+  return AETHER_ERR_INVALID;
 }
 
 }  // namespace aether

@@ -48,6 +48,8 @@ int32_t aether_device_ok(void);
  * gate_vid (both fp32 [B, N] with batch stride gate_bstride elements).
  * Output columns >= f16_from_col (a multiple of 8; < 0 = none) are written as fp16 instead of bf16 (used for
  * the V third of the fused QKV projection when the fp16-PV attention mode is on).
+ * M >= 1024 runs on CTA pairs (tcgen05 cta_group::2, cluster of two CTAs per 256 x 256 tile), smaller M on single
+ * CTAs; results are identical.  Environment variable AETHER_GEMM_1CTA=1 forces the single-CTA kernel (A/B timing).
  * Replaces nn.Linear inside CogVideoXBlock / CogVideoXPatchEmbed / proj_out (pipeline :865). */
 int aether_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int32_t M,
                      int32_t N, int32_t K, const float* bias, int32_t epilogue, const float* gate_vid,
@@ -55,8 +57,13 @@ int aether_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, voi
                      void* stream);
 
 /* out[B,S,H*64] (bf16) = softmax(Q K^T * softmax_scale) V over qkv[B,S,3,H,64], non-causal, head_dim 64.
- * Q, K are bf16; V is bf16 (v_fp16 = 0) or fp16 (v_fp16 = 1, selects the fp16-P / ex2.f16x2 / tensor-core
- * row-sum mode).  Replaces F.scaled_dot_product_attention in CogVideoXAttnProcessor2_0 (pipeline :865). */
+ * `v_fp16` is the kernel-variant id (all variants compute the same function to the tolerance of the tests):
+ *   0 baseline (P aliases S)   1, 2 fp16 P/V (the V third of qkv must then hold fp16 bit patterns; 2 adds a
+ *   polynomial exp2)   3 chunked two-pass softmax   4 sixteen softmax warps   5 decoupled S/P TMEM buffers
+ *   (product default)   6 per-warp pipelined softmax   7 one tile per CTA, two CTAs per SM   8 64-key tiles with
+ *   the S load in flight   9-11 mode 5 with 25 / 12.5 / 37.5 % polynomial exp2   12 three query tiles per CTA
+ *   13 mode 5 with interleaved consumers.  Any other id returns AETHER_ERR_INVALID.
+ * Replaces F.scaled_dot_product_attention in CogVideoXAttnProcessor2_0 (pipeline :865). */
 int aether_attention_bf16(const void* qkv, void* out, int32_t B, int32_t S, int32_t H, float softmax_scale,
                           int32_t v_fp16, void* stream);
 
@@ -104,7 +111,8 @@ typedef struct AetherDitConfig {
   int32_t flip_sin_to_cos;
   float freq_shift, norm_eps;
   int32_t ff_mult;
-  int32_t attention_fp16_pv;   /* 1: fp16 P/V + f16x2 exp attention mode (V emitted as fp16 by the QKV GEMM) */
+  int32_t attention_fp16_pv;   /* attention variant id passed to aether_attention_bf16 (5 = product default); for
+                                  ids 1 and 2 the QKV GEMM emits the V third as fp16 */
 } AetherDitConfig;
 
 typedef struct AetherDitLayerWeights {

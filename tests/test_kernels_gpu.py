@@ -174,6 +174,12 @@ def test_attention_peaked_and_flat_rows(v_fp16):
     _close(out, ref, 2 ** -6, 2e-2, f"attention peaked/flat fp16={v_fp16}")
 
 
+def test_attention_unknown_variant_rejected():
+    qkv = torch.zeros(1, 128, 3, 1, 64, device=DEV, dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError, match="AETHER_ERR_INVALID"):
+        _ops().attention(qkv, v_fp16=99)
+
+
 def test_gemm_fp16_columns():
     """Columns >= f16_from_col are emitted as fp16 (V third of the fused QKV projection)."""
     ops = _ops()
