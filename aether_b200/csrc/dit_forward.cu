@@ -17,6 +17,9 @@ namespace aether {
 int gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int M, int N, int K,
               const float* bias, int epilogue, const float* gate_vid, const float* gate_txt, int64_t gate_bstride,
               int S, int St, int f16_from_col, cudaStream_t stream);
+int gemm_qkv_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* qkv, int rows, int K, const float* bias,
+                  int S, int St, int H, const float* gq, const float* bq, const float* gk, const float* bk, float eps,
+                  const float* cosb, const float* sinb, int f16_from_col, cudaStream_t stream);
 int attention_bf16(const void* qkv, void* out, int B, int S, int H, float softmax_scale, int v_fp16,
                    cudaStream_t stream);
 int ln_modulate(const void* x, void* y, int B, int S, int St, int D, const float* gamma, const float* beta, float eps,
@@ -217,6 +220,14 @@ static int dit_forward_impl(AetherDit* h, const void* in0, int C0, int B0, const
   // ---- transformer blocks
   const int run_layers = (n_layers < 0 || n_layers > L) ? L : n_layers;
   const float softmax_scale = 1.0f / sqrtf(float(c.head_dim));
+  // AETHER_FUSED_QK=1 runs QK-LayerNorm + RoPE inside the QKV GEMM epilogue (aether_gemm_qkv_norm_rope_bf16).  Measured
+  // on B200 at S = 15076: 267.7 ms/step fused vs 264.5 ms with the separate qk_norm_rope launch -- four epilogue warps
+  // doing 64-wide LayerNorms with row-private cos/sin loads take longer than the 24.5k-clk main loop that should hide
+  // them, so the separate HBM-bound kernel (0.12 ms) stays the default until the epilogue runs on eight warps.
+  static const bool fused_qk = [] {
+    const char* e = getenv("AETHER_FUSED_QK");
+    return e != nullptr && e[0] == '1';
+  }();
   for (int l = 0; l < run_layers; ++l) {
     const AetherDitLayerWeights& lw = h->layers[l];
     // CogVideoXLayerNormZero chunk order: shift, scale, gate, enc_shift, enc_scale, enc_gate
@@ -224,10 +235,17 @@ static int dit_forward_impl(AetherDit* h, const void* in0, int C0, int B0, const
     const float* m2 = m1 + 6 * int64_t(D);
     RUN(ln_modulate(ws.hidden, ws.xn, B, S, St, D, lw.norm1_g, lw.norm1_b, c.norm_eps, nullptr, nullptr, m1, m1 + D,
                     m1 + 3 * D, m1 + 4 * D, mod_stride, stream));
-    RUN(gemm_bf16(ws.xn, D, lw.w_qkv, D, ws.qkv, 3 * D, rows, 3 * D, D, lw.b_qkv, 0, nullptr, nullptr, 0, 0, 0,
-                  (c.attention_fp16_pv == 1 || c.attention_fp16_pv == 2) ? 2 * D : -1, stream));
-    RUN(qk_norm_rope(ws.qkv, B, S, St, c.num_heads, lw.qn_g, lw.qn_b, lw.kn_g, lw.kn_b, 1e-6f, rope_cos, rope_sin,
-                     stream));
+    const int f16_from = (c.attention_fp16_pv == 1 || c.attention_fp16_pv == 2) ? 2 * D : -1;
+    if (fused_qk && c.head_dim == 64) {
+      // to_q/k/v + norm_q/norm_k + rotary embedding in ONE launch: LayerNorm(64) and RoPE run in the GEMM epilogue
+      RUN(gemm_qkv_bf16(ws.xn, D, lw.w_qkv, D, ws.qkv, rows, D, lw.b_qkv, S, St, c.num_heads, lw.qn_g, lw.qn_b, lw.kn_g,
+                        lw.kn_b, 1e-6f, rope_cos, rope_sin, f16_from, stream));
+    } else {
+      RUN(gemm_bf16(ws.xn, D, lw.w_qkv, D, ws.qkv, 3 * D, rows, 3 * D, D, lw.b_qkv, 0, nullptr, nullptr, 0, 0, 0, f16_from,
+                    stream));
+      RUN(qk_norm_rope(ws.qkv, B, S, St, c.num_heads, lw.qn_g, lw.qn_b, lw.kn_g, lw.kn_b, 1e-6f, rope_cos, rope_sin,
+                       stream));
+    }
     if (h->timing) AETHER_CUDA_OK(cudaEventRecord(h->ev[2 * l], stream));
     RUN(attention_bf16(ws.qkv, ws.attn, B, S, c.num_heads, softmax_scale, c.attention_fp16_pv, stream));
     if (h->timing) {

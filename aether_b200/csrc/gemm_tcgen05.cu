@@ -29,6 +29,7 @@ constexpr int C_BYTES = BM * CCHUNK * 2;
 constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 2 * C_BYTES + 256;
 constexpr int THREADS = 192;
 constexpr int GROUP_M = 8;
+constexpr int DH_QK = 64;                        // head_dim of the fused QKV epilogue (= CCHUNK: one chunk per head)
 
 struct Params {
   int M, N, K;
@@ -41,6 +42,11 @@ struct Params {
   __nv_bfloat16* C;         // EPI 2 reads the residual from C (in place)
   int64_t ldc;
   int f16_from;             // output columns >= f16_from are written as fp16 instead of bf16 (V third of QKV)
+  // EPI 3 (fused QKV projection): LayerNorm(64) of every q / k head + rotary embedding of the video tokens
+  const float* qn_g; const float* qn_b; const float* kn_g; const float* kn_b;   // [64] each
+  const float* rope_cos; const float* rope_sin;                                 // [S - St, 64] fp32 or null
+  float qk_eps;
+  int heads;                // N = 3 * heads * 64: columns [0, 64 heads) q, then k, then v
 };
 
 __device__ __forceinline__ void tile_coords(int t, const Params& p, int& m_blk, int& n_blk) {
@@ -87,6 +93,72 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const CUtensorMap
     tc_wait_ld();
 
     uint32_t packed[32];
+    if (EPI == 3 && n0 < 2 * p.heads * DH_QK) {
+      // One 64-column chunk = one q or k head of this thread's token: QK-LayerNorm and the rotary embedding happen on
+      // the accumulator row in registers, with the roundings and the summation order of the stand-alone
+      // qk_norm_rope kernel (dit_kernels.cu), which this path replaces inside the DiT (370 MB of HBM traffic and one
+      // launch per layer less).
+      const bool is_k = n0 >= p.heads * DH_QK;
+      float f[64];
+#pragma unroll
+      for (int c = 0; c < 64; ++c) {
+        float x = __uint_as_float(c < 32 ? v0[c] : v1[c - 32]);
+        if (p.bias != nullptr) x += __ldg(p.bias + n0 + c);
+        f[c] = __bfloat162float(__float2bfloat16_rn(x));     // the projection output is a bf16 tensor upstream
+      }
+      float part[8];
+#pragma unroll
+      for (int g8 = 0; g8 < 8; ++g8) {
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sum += f[g8 * 8 + j];
+        part[g8] = sum;
+      }
+      const float mean = (((part[0] + part[1]) + (part[2] + part[3])) + ((part[4] + part[5]) + (part[6] + part[7]))) *
+                         (1.0f / 64);
+#pragma unroll
+      for (int g8 = 0; g8 < 8; ++g8) {
+        float sq = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float d = f[g8 * 8 + j] - mean;
+          sq += d * d;
+        }
+        part[g8] = sq;
+      }
+      const float sq = ((part[0] + part[1]) + (part[2] + part[3])) + ((part[4] + part[5]) + (part[6] + part[7]));
+      const float rstd = rsqrtf(sq * (1.0f / 64) + p.qk_eps);
+      const float* g = is_k ? p.kn_g : p.qn_g;
+      const float* bt = is_k ? p.kn_b : p.qn_b;
+#pragma unroll
+      for (int c = 0; c < 64; ++c) f[c] = (f[c] - mean) * rstd;
+#pragma unroll
+      for (int c = 0; c < 64; c += 4) {
+        const float4 gm = __ldg(reinterpret_cast<const float4*>(g + c));
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(bt + c));
+        f[c] = f[c] * gm.x + bb.x; f[c + 1] = f[c + 1] * gm.y + bb.y;
+        f[c + 2] = f[c + 2] * gm.z + bb.z; f[c + 3] = f[c + 3] * gm.w + bb.w;
+      }
+      const int tok = row_ok ? row % p.S : 0;
+      if (p.rope_cos != nullptr && tok >= p.St) {
+        const float* cr = p.rope_cos + int64_t(tok - p.St) * 64;
+        const float* sr = p.rope_sin + int64_t(tok - p.St) * 64;
+#pragma unroll
+        for (int c = 0; c < 64; c += 4) {
+          const float4 cs = __ldg(reinterpret_cast<const float4*>(cr + c));
+          const float4 sn = __ldg(reinterpret_cast<const float4*>(sr + c));
+          // upstream rounds LayerNorm's output to bf16 before apply_rotary_emb upcasts it again
+          const float a0 = __bfloat162float(__float2bfloat16_rn(f[c])), a1 = __bfloat162float(__float2bfloat16_rn(f[c + 1]));
+          const float a2 = __bfloat162float(__float2bfloat16_rn(f[c + 2])), a3 = __bfloat162float(__float2bfloat16_rn(f[c + 3]));
+          f[c] = a0 * cs.x - a1 * sn.x;
+          f[c + 1] = a1 * cs.y + a0 * sn.y;
+          f[c + 2] = a2 * cs.z - a3 * sn.z;
+          f[c + 3] = a3 * cs.w + a2 * sn.w;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 32; ++c) packed[c] = pack_bf16x2(f[2 * c], f[2 * c + 1]);
+    } else {
 #pragma unroll
     for (int g8 = 0; g8 < 8; ++g8) {     // 8 groups of 8 columns (one 16-byte bf16 vector each)
       float x[8];
@@ -125,6 +197,7 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const CUtensorMap
 #pragma unroll
         for (int j = 0; j < 4; ++j) packed[g8 * 4 + j] = pack_bf16x2(x[2 * j], x[2 * j + 1]);
       }
+    }
     }
     // staging buffer `cbuf` was last used two chunks ago; make sure that TMA store has read it
     if (store_leader) tma_store_wait_read<1>();
@@ -471,13 +544,15 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, 
 }
 }  // namespace gemm
 
-int gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int M, int N, int K,
-              const float* bias, int epilogue, const float* gate_vid, const float* gate_txt, int64_t gate_bstride,
-              int S, int St, int f16_from_col, cudaStream_t stream) {
+// `qk` (epilogue 3 only) carries the QK-LayerNorm / rotary fields of Params.
+static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int M, int N, int K,
+                     const float* bias, int epilogue, const float* gate_vid, const float* gate_txt,
+                     int64_t gate_bstride, int S, int St, int f16_from_col, const gemm::Params* qk,
+                     cudaStream_t stream) {
   AETHER_CHECK_ARG(M > 0 && N > 0 && K > 0);
   AETHER_CHECK_ARG(f16_from_col < 0 || f16_from_col % 8 == 0);
   AETHER_CHECK_ARG(N % 8 == 0 && K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldc % 8 == 0);
-  AETHER_CHECK_ARG(epilogue >= 0 && epilogue <= 2);
+  AETHER_CHECK_ARG(epilogue >= 0 && epilogue <= 3 && (epilogue == 3) == (qk != nullptr));
   AETHER_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(C) & 15) == 0);
   if (epilogue == 2) AETHER_CHECK_ARG(gate_vid != nullptr && gate_txt != nullptr && S > 0);
@@ -496,6 +571,12 @@ int gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, i
   p.C = reinterpret_cast<__nv_bfloat16*>(C);
   p.ldc = ldc;
   p.f16_from = f16_from_col < 0 ? 0x7fffffff : f16_from_col;
+  p.qn_g = p.qn_b = p.kn_g = p.kn_b = p.rope_cos = p.rope_sin = nullptr;
+  p.qk_eps = 0.f; p.heads = 0;
+  if (qk != nullptr) {
+    p.qn_g = qk->qn_g; p.qn_b = qk->qn_b; p.kn_g = qk->kn_g; p.kn_b = qk->kn_b;
+    p.rope_cos = qk->rope_cos; p.rope_sin = qk->rope_sin; p.qk_eps = qk->qk_eps; p.heads = qk->heads;
+  }
   // Large problems run on CTA pairs (cta_group::2); AETHER_GEMM_1CTA=1 forces the single-CTA kernel for A/B timing.
   static const bool force_1cta = [] {
     const char* e = getenv("AETHER_GEMM_1CTA");
@@ -509,17 +590,51 @@ int gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, i
     switch (epilogue) {
       case 0: return gemm::launch2<0>(ta, tbh, tc, p2, stream);
       case 1: return gemm::launch2<1>(ta, tbh, tc, p2, stream);
-      default: return gemm::launch2<2>(ta, tbh, tc, p2, stream);
+      case 2: return gemm::launch2<2>(ta, tbh, tc, p2, stream);
+      default: return gemm::launch2<3>(ta, tbh, tc, p2, stream);
     }
   }
   switch (epilogue) {
     case 0: return gemm::launch<0>(ta, tb, tc, p, stream);
     case 1: return gemm::launch<1>(ta, tb, tc, p, stream);
-    default: return gemm::launch<2>(ta, tb, tc, p, stream);
+    case 2: return gemm::launch<2>(ta, tb, tc, p, stream);
+    default: return gemm::launch<3>(ta, tb, tc, p, stream);
   }
 }
 
+int gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int M, int N, int K,
+              const float* bias, int epilogue, const float* gate_vid, const float* gate_txt, int64_t gate_bstride,
+              int S, int St, int f16_from_col, cudaStream_t stream) {
+  AETHER_CHECK_ARG(epilogue >= 0 && epilogue <= 2);
+  return gemm_impl(A, lda, W, ldw, C, ldc, M, N, K, bias, epilogue, gate_vid, gate_txt, gate_bstride, S, St,
+                   f16_from_col, nullptr, stream);
+}
+
+// Fused QKV projection: qkv[rows, 3*H*64] = A . W^T + bias, then QK-LayerNorm(64) on every q / k head and the rotary
+// embedding on the video tokens (s >= St), all inside the GEMM epilogue (bit-compatible with gemm_bf16 followed by
+// qk_norm_rope).  Replaces to_q / to_k / to_v + norm_q / norm_k + apply_rotary_emb of CogVideoXAttnProcessor2_0.
+int gemm_qkv_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* qkv, int rows, int K, const float* bias,
+                  int S, int St, int H, const float* gq, const float* bq, const float* gk, const float* bk, float eps,
+                  const float* cosb, const float* sinb, int f16_from_col, cudaStream_t stream) {
+  AETHER_CHECK_ARG(H > 0 && S > 0 && St >= 0 && gq && bq && gk && bk);
+  AETHER_CHECK_ARG((cosb == nullptr) == (sinb == nullptr));
+  gemm::Params qk{};
+  qk.qn_g = gq; qk.qn_b = bq; qk.kn_g = gk; qk.kn_b = bk;
+  qk.rope_cos = cosb; qk.rope_sin = sinb; qk.qk_eps = eps; qk.heads = H;
+  const int N = 3 * H * gemm::DH_QK;
+  return gemm_impl(A, lda, W, ldw, qkv, N, rows, N, K, bias, 3, nullptr, nullptr, 0, S, St, f16_from_col, &qk, stream);
+}
+
 }  // namespace aether
+
+extern "C" int aether_gemm_qkv_norm_rope_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* qkv,
+                                              int32_t rows, int32_t K, const float* bias, int32_t S, int32_t St,
+                                              int32_t H, const float* qn_g, const float* qn_b, const float* kn_g,
+                                              const float* kn_b, float eps, const float* rope_cos,
+                                              const float* rope_sin, int32_t f16_from_col, void* stream) {
+  return aether::gemm_qkv_bf16(A, lda, W, ldw, qkv, rows, K, bias, S, St, H, qn_g, qn_b, kn_g, kn_b, eps, rope_cos,
+                               rope_sin, f16_from_col, reinterpret_cast<cudaStream_t>(stream));
+}
 
 extern "C" int aether_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc,
                                 int32_t M, int32_t N, int32_t K, const float* bias, int32_t epilogue,

@@ -90,6 +90,27 @@ def qk_norm_rope(qkv, gq, bq, gk, bk, eps=1e-6, cos=None, sin=None, St=0):
     return qkv
 
 
+def gemm_qkv_norm_rope(x, w, bias, B, S, St, H, gq, bq, gk, bk, eps=1e-6, cos=None, sin=None, f16_from_col=-1):
+    """x [B*S, K] bf16, w [3*H*64, K] bf16 -> qkv [B, S, 3, H, 64] bf16 with q / k already QK-LayerNorm'ed and rotated
+    (the fused epilogue of the QKV projection; same values as gemm(...) followed by qk_norm_rope(...))."""
+    lib = _lib.require_device()
+    _need(x, BF16, "x"); _need(w, BF16, "w")
+    rows, K = x.shape
+    assert rows == B * S and w.shape[0] == 3 * H * 64
+    for t in (gq, bq, gk, bk):
+        _need(t, F32, "qk norm param")
+    if bias is not None:
+        _need(bias, F32, "bias")
+    if cos is not None:
+        _need(cos, F32, "cos"); _need(sin, F32, "sin")
+        assert cos.shape == (S - St, 64)
+    qkv = torch.empty(B, S, 3, H, 64, dtype=BF16, device=x.device)
+    check(lib.aether_gemm_qkv_norm_rope_bf16(ptr(x), x.stride(0), ptr(w), w.stride(0), ptr(qkv), rows, K, ptr(bias), S, St,
+                                             H, ptr(gq), ptr(bq), ptr(gk), ptr(bk), float(eps), ptr(cos), ptr(sin),
+                                             f16_from_col, current_stream()), "gemm_qkv_norm_rope_bf16")
+    return qkv
+
+
 def small_m_linear(x, w, bias=None, act=0):
     lib = _lib.require_device()
     _need(x, F32, "x"); _need(w, BF16, "w")

@@ -328,8 +328,12 @@ class AetherTransformer3D(nn.Module):
         return ms.value, n.value
 
     def launches_per_forward(self, batch: int) -> int:
-        """Kernels of this library launched by one forward (see csrc/dit_forward.cu)."""
-        return 4 + 1 + 2 * batch + 8 * self.config.num_layers + 1 + batch + 1
+        """Kernels of this library launched by one forward (see csrc/dit_forward.cu): 8 per layer (LN-modulate, QKV,
+        QK-norm+RoPE, attention, to_out, LN-modulate, FF1, FF2); 7 with AETHER_FUSED_QK=1 (QK-norm+RoPE in the QKV
+        epilogue)."""
+        import os
+        per_layer = 7 if os.environ.get("AETHER_FUSED_QK", "0")[:1] == "1" and self.config.attention_head_dim == 64 else 8
+        return 4 + 1 + 2 * batch + per_layer * self.config.num_layers + 1 + batch + 1
 
     # ------------------------------------------------------------------ loop form: concat / repeat / expand folded in
     @torch.no_grad()

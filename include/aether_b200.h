@@ -56,6 +56,16 @@ int aether_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, voi
                      const float* gate_txt, int64_t gate_bstride, int32_t S, int32_t St, int32_t f16_from_col,
                      void* stream);
 
+/* Fused QKV projection: qkv[rows, 3*H*64] = A[rows,K] . W[3*H*64,K]^T + bias, followed INSIDE the GEMM epilogue by
+ * QK-LayerNorm(64) of every q and k head (gamma/beta fp32 [64]) and the rotary embedding of the video tokens
+ * (token s = row % S >= St; rope_cos / rope_sin fp32 [S - St, 64], both NULL = no rotary embedding).  Same values as
+ * aether_gemm_bf16 followed by aether_qk_norm_rope.  Replaces to_q/to_k/to_v + norm_q/norm_k + apply_rotary_emb of
+ * CogVideoXAttnProcessor2_0 (pipeline :865). */
+int aether_gemm_qkv_norm_rope_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* qkv, int32_t rows,
+                                   int32_t K, const float* bias, int32_t S, int32_t St, int32_t H, const float* qn_g,
+                                   const float* qn_b, const float* kn_g, const float* kn_b, float eps,
+                                   const float* rope_cos, const float* rope_sin, int32_t f16_from_col, void* stream);
+
 /* out[B,S,H*64] (bf16) = softmax(Q K^T * softmax_scale) V over qkv[B,S,3,H,64], non-causal, head_dim 64.
  * `v_fp16` is the kernel-variant id (all variants compute the same function to the tolerance of the tests):
  *   0 baseline (P aliases S)   1, 2 fp16 P/V (the V third of qkv must then hold fp16 bit patterns; 2 adds a

@@ -174,6 +174,30 @@ def test_attention_peaked_and_flat_rows(v_fp16):
     _close(out, ref, 2 ** -6, 2e-2, f"attention peaked/flat fp16={v_fp16}")
 
 
+@pytest.mark.parametrize("B,S,St,H,K", [(1, 300, 18, 2, 128), (2, 700, 226, 4, 256), (1, 1500, 226, 6, 192)])
+def test_fused_qkv_projection_equals_gemm_then_qk_norm_rope(B, S, St, H, K):
+    """The QKV GEMM with QK-LayerNorm + RoPE in its epilogue against the two separate kernels it replaces (single-CTA
+    and CTA-pair kernels: rows = B*S below and above 1024).  Same roundings and summation order => identical output
+    up to the rare contraction difference (<= 1 bf16 ulp on a handful of elements)."""
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(B * 1000 + S + H)
+    x = torch.randn(B * S, K, device=DEV, generator=g).bfloat16()
+    w = (torch.randn(3 * H * 64, K, device=DEV, generator=g) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(3 * H * 64, device=DEV, generator=g) * 0.3
+    gq, gk = (1 + 0.2 * torch.randn(64, device=DEV, generator=g) for _ in range(2))
+    bq, bk = (0.1 * torch.randn(64, device=DEV, generator=g) for _ in range(2))
+    cos = torch.rand(S - St, 64, device=DEV, generator=g) * 2 - 1
+    sin = torch.rand(S - St, 64, device=DEV, generator=g) * 2 - 1
+    ref = ops.gemm(x, w, bias, 0).view(B, S, 3, H, 64).clone()
+    ops.qk_norm_rope(ref, gq, bq, gk, bk, 1e-6, cos, sin, St)
+    out = ops.gemm_qkv_norm_rope(x, w, bias, B, S, St, H, gq, bq, gk, bk, 1e-6, cos, sin)
+    assert torch.equal(out[:, :, 2], ref[:, :, 2])                       # V third: plain projection
+    diff = (out.float() - ref.float()).abs()
+    ulp = ref.float().abs().clamp_min(2 ** -6) * 2 ** -7
+    assert (diff <= ulp).all(), f"max diff {diff.max().item()}"
+    assert (diff > 0).float().mean().item() < 1e-3
+
+
 def test_attention_unknown_variant_rejected():
     qkv = torch.zeros(1, 128, 3, 1, 64, device=DEV, dtype=torch.bfloat16)
     with pytest.raises(RuntimeError, match="AETHER_ERR_INVALID"):
