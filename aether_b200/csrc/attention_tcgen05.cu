@@ -446,6 +446,10 @@ int attention_v2_launch(const CUtensorMap& tm, int B, int S, int H, void* out, f
 int attention_v3_launch(const CUtensorMap& tm, int B, int S, int H, void* out, float scale_log2, int pipelined,
                         cudaStream_t stream);
 int attention_v4_launch(const CUtensorMap& tm, int B, int S, int H, void* out, float scale_log2, cudaStream_t stream);
+int attention_v3_launch_blocks(const CUtensorMap& tm, int B, int S, int H, void* out, float scale_log2, int variant,
+                               int q_blocks, cudaStream_t stream);
+int attention_v4_launch_rows(const CUtensorMap& tm, int B, int S, int H, void* out, float scale_log2, int q_row0,
+                             cudaStream_t stream);
 int attention_v5_launch(const void* qkv, int B, int S, int H, void* out, float scale_log2, cudaStream_t stream);
 int attention_v6_launch(const void* qkv, int B, int S, int H, void* out, float scale_log2, cudaStream_t stream);
 
@@ -477,13 +481,42 @@ int attention_bf16(const void* qkv, void* out, int B, int S, int H, float softma
     case 9: return attention_v3_launch(tm, B, S, H, out, p.scale_log2, 2, stream);   // mode 5 + 25 % polynomial exp2
     case 10: return attention_v3_launch(tm, B, S, H, out, p.scale_log2, 3, stream);  // 12.5 %
     case 11: return attention_v3_launch(tm, B, S, H, out, p.scale_log2, 4, stream);  // 37.5 %
+    case 14: {
+      // Split schedule: the complete 256-row query blocks on the mode-5 kernel, the ragged rest (S % 256 rows) as
+      // 128-row CTAs of the mode-7 kernel on a side stream.  The block scheduler drains the main grid first, so the
+      // tail CTAs land on the SMs the last, partially filled wave leaves idle (S = 15076, 48 heads: 2832 CTAs = 19.1
+      // waves become 2784 = 18.8 waves plus 96 half-size CTAs that run alongside the last wave).
+      const int full = S / (2 * attn::BQ);
+      if (full == 0 || S == full * 2 * attn::BQ) return attention_v3_launch(tm, B, S, H, out, p.scale_log2, 0, stream);
+      struct Side {
+        cudaStream_t s = nullptr;
+        cudaEvent_t fork = nullptr, join = nullptr;
+        bool ok = false;
+        Side() {
+          ok = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) == cudaSuccess &&
+               cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) == cudaSuccess &&
+               cudaEventCreateWithFlags(&join, cudaEventDisableTiming) == cudaSuccess;
+        }
+      };
+      static Side side;
+      if (!side.ok) return AETHER_ERR_CUDA;
+      AETHER_CUDA_OK(cudaEventRecord(side.fork, stream));
+      AETHER_CUDA_OK(cudaStreamWaitEvent(side.s, side.fork, 0));
+      rc = attention_v3_launch_blocks(tm, B, S, H, out, p.scale_log2, 0, full, stream);
+      if (rc) return rc;
+      rc = attention_v4_launch_rows(tm, B, S, H, out, p.scale_log2, full * 2 * attn::BQ, side.s);
+      if (rc) return rc;
+      AETHER_CUDA_OK(cudaEventRecord(side.join, side.s));
+      AETHER_CUDA_OK(cudaStreamWaitEvent(stream, side.join, 0));
+      return AETHER_OK;
+    }
     case 13: return attention_v3_launch(tm, B, S, H, out, p.scale_log2, 5, stream);  // mode 5, consumers interleaved
     case 12: return attention_v6_launch(qkv, B, S, H, out, p.scale_log2, stream);    // 3 query tiles, 12 softmax warps
     case 8: return attention_v5_launch(qkv, B, S, H, out, p.scale_log2, stream);     // 64-key tiles, S load in flight
     case 3: return attn::launch<3>(tm, p, grid, stream);    // bf16 V, chunked two-pass softmax
     default: break;
   }
-  AETHER_CHECK_ARG(!"unknown attention variant id (v_fp16 must be 0..13)");
+  AETHER_CHECK_ARG(!"unknown attention variant id (v_fp16 must be 0..14)");
   return AETHER_ERR_INVALID;
 }
 

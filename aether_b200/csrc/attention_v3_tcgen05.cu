@@ -504,8 +504,16 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Params p
 
 }  // namespace attn3
 
+int attention_v3_launch_blocks(const CUtensorMap& tm, int B, int S, int H, void* out, float scale_log2, int variant,
+                               int q_blocks, cudaStream_t stream);
 int attention_v3_launch(const CUtensorMap& tm, int B, int S, int H, void* out, float scale_log2, int variant,
                         cudaStream_t stream) {
+  return attention_v3_launch_blocks(tm, B, S, H, out, scale_log2, variant, (int)ceil_div(S, 2 * attn3::BQ), stream);
+}
+
+// Only the first `q_blocks` 256-row query blocks (all keys): the main launch of the split mode-5 schedule.
+int attention_v3_launch_blocks(const CUtensorMap& tm, int B, int S, int H, void* out, float scale_log2, int variant,
+                               int q_blocks, cudaStream_t stream) {
   // variant: 0 = mode 5, 1 = mode 6 (pipelined softmax), 2/3/4 = mode 5 with 25 % / 12.5 % / 37.5 % polynomial exp2
   using Kernel = void (*)(const CUtensorMap, const attn3::Params);
   static const Kernel kernels[6] = {attn3::attention_v3_kernel<false, 0>, attn3::attention_v3_kernel<true, 0>,
@@ -522,7 +530,8 @@ int attention_v3_launch(const CUtensorMap& tm, int B, int S, int H, void* out, f
   p.B = B; p.H = H; p.S = S;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.scale_log2 = scale_log2;
-  dim3 grid((unsigned)ceil_div(S, 2 * attn3::BQ), (unsigned)H, (unsigned)B);
+  AETHER_CHECK_ARG(q_blocks > 0 && q_blocks <= (int)ceil_div(S, 2 * attn3::BQ));
+  dim3 grid((unsigned)q_blocks, (unsigned)H, (unsigned)B);
   kernels[variant]<<<grid, attn3::THREADS, attn3::SMEM_BYTES, stream>>>(tm, p);
   AETHER_CUDA_OK(cudaGetLastError());
   return AETHER_OK;

@@ -22,6 +22,7 @@ struct Params {
   int B, H, S;
   __nv_bfloat16* out;
   float scale_log2;
+  int q_row0;      // first query row this launch covers (the tail launch of mode 5 starts at a multiple of 256)
 };
 
 __global__ void __launch_bounds__(THREADS, 2)
@@ -47,7 +48,7 @@ attention_v4_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Params p
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform (see gemm_tcgen05.cu)
   const int lane = threadIdx.x & 31;
   const int q_blk = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int q0 = q_blk * BQ;
+  const int q0 = p.q_row0 + q_blk * BQ;
   const int n_kv = (p.S + BKV - 1) / BKV;
   const int H = p.H;
 
@@ -293,7 +294,15 @@ attention_v4_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Params p
 
 }  // namespace attn4
 
+int attention_v4_launch_rows(const CUtensorMap& tm, int B, int S, int H, void* out, float scale_log2, int q_row0,
+                             cudaStream_t stream);
 int attention_v4_launch(const CUtensorMap& tm, int B, int S, int H, void* out, float scale_log2, cudaStream_t stream) {
+  return attention_v4_launch_rows(tm, B, S, H, out, scale_log2, 0, stream);
+}
+
+// Query rows [q_row0, S) only (all keys): the tail launch of the split mode-5 schedule.
+int attention_v4_launch_rows(const CUtensorMap& tm, int B, int S, int H, void* out, float scale_log2, int q_row0,
+                             cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     AETHER_CUDA_OK(cudaFuncSetAttribute(attn4::attention_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -304,7 +313,9 @@ int attention_v4_launch(const CUtensorMap& tm, int B, int S, int H, void* out, f
   p.B = B; p.H = H; p.S = S;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.scale_log2 = scale_log2;
-  dim3 grid((unsigned)ceil_div(S, attn4::BQ), (unsigned)H, (unsigned)B);
+  p.q_row0 = q_row0;
+  AETHER_CHECK_ARG(q_row0 >= 0 && q_row0 < S);
+  dim3 grid((unsigned)ceil_div(S - q_row0, attn4::BQ), (unsigned)H, (unsigned)B);
   attn4::attention_v4_kernel<<<grid, attn4::THREADS, attn4::SMEM_BYTES, stream>>>(tm, p);
   AETHER_CUDA_OK(cudaGetLastError());
   return AETHER_OK;

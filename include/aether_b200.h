@@ -72,7 +72,8 @@ int aether_gemm_qkv_norm_rope_bf16(const void* A, int64_t lda, const void* W, in
  *   polynomial exp2)   3 chunked two-pass softmax   4 sixteen softmax warps   5 decoupled S/P TMEM buffers
  *   (product default)   6 per-warp pipelined softmax   7 one tile per CTA, two CTAs per SM   8 64-key tiles with
  *   the S load in flight   9-11 mode 5 with 25 / 12.5 / 37.5 % polynomial exp2   12 three query tiles per CTA
- *   13 mode 5 with interleaved consumers.  Any other id returns AETHER_ERR_INVALID.
+ *   13 mode 5 with interleaved consumers   14 mode 5 on the complete 256-row blocks + mode 7 on the ragged rest
+ *   (side stream).  Any other id returns AETHER_ERR_INVALID.
  * Replaces F.scaled_dot_product_attention in CogVideoXAttnProcessor2_0 (pipeline :865). */
 int aether_attention_bf16(const void* qkv, void* out, int32_t B, int32_t S, int32_t H, float softmax_scale,
                           int32_t v_fp16, void* stream);
