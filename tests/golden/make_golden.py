@@ -131,6 +131,9 @@ def make_sliding():
     run(57, 480, 720, "temporal")        # 3 temporal windows, no spatial tiling (windows stay fp32)
     run(49, 480, 853, "horizontal")      # 2 temporal x 2 horizontal tiles (overlap 587 px)
     run(41, 600, 720, "vertical")        # 1 temporal x 2 vertical tiles
+    run(129, 480, 853, "long")           # 12 temporal x 2 horizontal = 24 tiles: the chain of BASELINE configs[4]
+    #                                      (512 frames -> 60 x 2 tiles) at a quarter of its length, incl. the
+    #                                      irregular last window at t - 41
 
 
 def make_pipeline():

@@ -86,7 +86,7 @@ def test_compute_scale_matches_reference(golden_dir):
     assert float(g["c3__scale"]) == 0.0           # zero denominator -> 0 (postprocess_utils.py:858-862)
 
 
-@pytest.mark.parametrize("name", ["temporal", "horizontal", "vertical"])
+@pytest.mark.parametrize("name", ["temporal", "horizontal", "vertical", "long"])
 def test_tile_plan_and_blend_match_reference(golden_dir, name):
     from aether_b200.sliding_window import plan_windows
     from oracle.blend import blend_all

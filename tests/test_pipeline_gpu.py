@@ -79,7 +79,7 @@ def test_pipeline_matches_reference_golden(golden_dir, name, kw):
     assert rel_ray <= 6e-2
 
 
-@pytest.mark.parametrize("name", ["temporal", "horizontal", "vertical"])
+@pytest.mark.parametrize("name", ["temporal", "horizontal", "vertical", "long"])
 def test_device_blend_matches_reference_golden(golden_dir, name):
     from aether_b200.sliding_window import process_with_sliding_window
     g = np.load(golden_dir / f"sliding_{name}.npz")

@@ -26,7 +26,7 @@ def main():
     torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
     dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
     ok = True
-    for name in ("temporal", "horizontal", "vertical"):
+    for name in ("temporal", "horizontal", "vertical", "long"):
         g = np.load(ROOT / "tests" / "golden" / f"sliding_{name}.npz")
         t, h, w = g["thw"].tolist()
         obs = synthetic_long_clip(t, h, w)
