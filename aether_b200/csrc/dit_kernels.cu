@@ -251,24 +251,13 @@ generic:
 
 // ------------------------------------------------------------------------------------------------
 // QK-LayerNorm(64) + 3-D RoPE, in place on the q and k thirds of qkv[B,S,3,H,64].
-// 8 threads per (token, head) vector of 64 (one 16-byte vector each); grid.y = token, grid.x covers
-// the 2*H head-vectors of the token.  Algorithmic bytes: 2 * (2/3) * |qkv|  (+ cos/sin, L2-resident).
+// 8 threads per (token, head) vector of 64 (one 16-byte vector each).  Every thread handles the q vector AND the k
+// vector of the same (token, head, sub-vector): two independent 16-byte loads are in flight before any math and the
+// token's cos/sin row is fetched once for both.  grid.y = token, grid.x covers the H head-vectors.
+// Algorithmic bytes: 2 * (2/3) * |qkv|  (+ cos/sin, L2-resident).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-qk_norm_rope_kernel(__nv_bfloat16* __restrict__ qkv, int S, int St, int H, const float* __restrict__ gq,
-                    const float* __restrict__ bq, const float* __restrict__ gk, const float* __restrict__ bk,
-                    float eps, const float* __restrict__ cosb, const float* __restrict__ sinb) {
-  const int token = blockIdx.y;                     // b * S + s
-  const int s = token % S;
-  const int vec = blockIdx.x * 256 + threadIdx.x;   // 16-byte vector index inside the q|k span of the token
-  const int nvec = 2 * H * 8;
-  if (vec >= nvec) return;
-  const int hv = vec >> 3;                          // head-vector: [0,H) = q heads, [H,2H) = k heads
-  const int sub = vec & 7;                          // which 8 of the 64 elements
-  const bool is_k = hv >= H;
-  uint4* ptr = reinterpret_cast<uint4*>(qkv + int64_t(token) * (3 * H * 64)) + vec;
-  float f[8];
-  unpack8(*ptr, f);
+__device__ __forceinline__ void qk_norm_vec(float (&f)[8], const float* __restrict__ g, const float* __restrict__ bt,
+                                            int sub, float eps) {
   float sum = 0.f;
 #pragma unroll
   for (int j = 0; j < 8; ++j) sum += f[j];
@@ -286,40 +275,60 @@ qk_norm_rope_kernel(__nv_bfloat16* __restrict__ qkv, int S, int St, int H, const
   sq += __shfl_xor_sync(0xffffffffu, sq, 2);
   sq += __shfl_xor_sync(0xffffffffu, sq, 4);
   const float rstd = rsqrtf(sq * (1.0f / 64) + eps);
-  const float* g = is_k ? gk : gq;
-  const float* bt = is_k ? bk : bq;
 #pragma unroll
   for (int j = 0; j < 8; ++j) f[j] = (f[j] - mean) * rstd;
-  {
-    float gm[8], bb[8];
-    load8(g + sub * 8, gm);
-    load8(bt + sub * 8, bb);
+  float gm[8], bb[8];
+  load8(g + sub * 8, gm);
+  load8(bt + sub * 8, bb);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = f[j] * gm[j] + bb[j];
+  for (int j = 0; j < 8; ++j) f[j] = f[j] * gm[j] + bb[j];
+}
+__device__ __forceinline__ void rope_vec(float (&f)[8], const float (&c)[8], const float (&sn)[8]) {
+  // upstream rounds LayerNorm's output to bf16 before apply_rotary_emb upcasts it again
+#pragma unroll
+  for (int j = 0; j < 8; ++j) f[j] = __bfloat162float(__float2bfloat16_rn(f[j]));
+#pragma unroll
+  for (int j = 0; j < 8; j += 2) {
+    const float xr = f[j], xi = f[j + 1];
+    f[j] = xr * c[j] - xi * sn[j];
+    f[j + 1] = xi * c[j + 1] + xr * sn[j + 1];
   }
+}
+
+__global__ void __launch_bounds__(128)
+qk_norm_rope_kernel(__nv_bfloat16* __restrict__ qkv, int S, int St, int H, const float* __restrict__ gq,
+                    const float* __restrict__ bq, const float* __restrict__ gk, const float* __restrict__ bk,
+                    float eps, const float* __restrict__ cosb, const float* __restrict__ sinb) {
+  const int token = blockIdx.y;                     // b * S + s
+  const int s = token % S;
+  const int vec = blockIdx.x * 128 + threadIdx.x;   // 16-byte vector index inside the q span of the token
+  if (vec >= H * 8) return;                         // whole warps only (H even)
+  const int sub = vec & 7;                          // which 8 of the 64 elements
+  uint4* qp = reinterpret_cast<uint4*>(qkv + int64_t(token) * (3 * H * 64)) + vec;
+  uint4* kp = qp + H * 8;
+  const uint4 qraw = *qp, kraw = *kp;               // both loads issued before the first use
+  float fq[8], fk[8];
+  unpack8(qraw, fq);
+  unpack8(kraw, fk);
+  qk_norm_vec(fq, gq, bq, sub, eps);
+  qk_norm_vec(fk, gk, bk, sub, eps);
   if (cosb != nullptr && s >= St) {
-    // upstream rounds LayerNorm's output to bf16 before apply_rotary_emb upcasts it again
-#pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = __bfloat162float(__float2bfloat16_rn(f[j]));
     float c[8], sn[8];
     load8(cosb + int64_t(s - St) * 64 + sub * 8, c);
     load8(sinb + int64_t(s - St) * 64 + sub * 8, sn);
-#pragma unroll
-    for (int j = 0; j < 8; j += 2) {
-      const float xr = f[j], xi = f[j + 1];
-      f[j] = xr * c[j] - xi * sn[j];
-      f[j + 1] = xi * c[j + 1] + xr * sn[j + 1];
-    }
+    rope_vec(fq, c, sn);
+    rope_vec(fk, c, sn);
   }
-  *ptr = pack8(f);
+  *qp = pack8(fq);
+  *kp = pack8(fk);
 }
 
 int qk_norm_rope(void* qkv, int B, int S, int St, int H, const float* gq, const float* bq, const float* gk,
                  const float* bk, float eps, const float* cosb, const float* sinb, cudaStream_t stream) {
   AETHER_CHECK_ARG(B > 0 && S > 0 && H > 0 && gq && bq && gk && bk);
   AETHER_CHECK_ARG((cosb == nullptr) == (sinb == nullptr));
-  dim3 grid((unsigned)ceil_div(2 * H * 8, 256), (unsigned)(B * S));
-  qk_norm_rope_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<__nv_bfloat16*>(qkv), S, St, H, gq, bq, gk, bk, eps,
+  dim3 grid((unsigned)ceil_div(H * 8, 128), (unsigned)(B * S));
+  qk_norm_rope_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<__nv_bfloat16*>(qkv), S, St, H, gq, bq, gk, bk, eps,
                                                 cosb, sinb);
   AETHER_CUDA_OK(cudaGetLastError());
   return AETHER_OK;
