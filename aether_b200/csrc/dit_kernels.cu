@@ -126,7 +126,7 @@ ln_modulate_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restric
 // of the current (batch, text|video) segment are staged ONCE per block in shared memory (2 * D fp32), so a row
 // costs 12 KB of HBM traffic and no parameter re-reads from L1/L2 (the generic kernel re-reads 4 vectors per row).
 template <int VPL>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 ln_modulate_smem_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int S, int St,
                         const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                         const float* __restrict__ shift_vid, const float* __restrict__ scale_vid,
@@ -155,23 +155,32 @@ ln_modulate_smem_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __re
     for (int r = blockIdx.x * 8 + warp; r < nrows; r += gridDim.x * 8) {
       const int64_t row = int64_t(r0 + r);
       const uint4* xr = reinterpret_cast<const uint4*>(x + row * D);
-      float v[VPL][8];
+      // The row stays PACKED in registers (VPL x 16 bytes) and is widened three times (sum, squares, output): the
+      // fp32 copy cost 214 registers at D = 3072 and left ONE 8-warp block per SM; packed (and with the launch bound
+      // that stops ptxas from caching the widened values) two blocks are resident.
+      uint4 raw[VPL];
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) raw[i] = xr[i * 32 + lane];
       float sum = 0.f;
 #pragma unroll
       for (int i = 0; i < VPL; ++i) {
-        unpack8(xr[i * 32 + lane], v[i]);
+        float v[8];
+        unpack8(raw[i], v);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) sum += v[i][j];
+        for (int j = 0; j < 8; ++j) sum += v[j];
       }
       const float mean = warp_sum(sum) * (1.0f / D);
       float sq = 0.f;
 #pragma unroll
-      for (int i = 0; i < VPL; ++i)
+      for (int i = 0; i < VPL; ++i) {
+        float v[8];
+        unpack8(raw[i], v);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float d = v[i][j] - mean;
+          const float d = v[j] - mean;
           sq += d * d;
         }
+      }
       const float rstd = rsqrtf(warp_sum(sq) * (1.0f / D) + eps);
       uint4* yr = reinterpret_cast<uint4*>(y + row * D);
 #pragma unroll
@@ -179,11 +188,12 @@ ln_modulate_smem_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __re
         const int c = (i * 32 + lane) * 8;
         const float4 a0 = *reinterpret_cast<const float4*>(sA + c), a1 = *reinterpret_cast<const float4*>(sA + c + 4);
         const float4 b0 = *reinterpret_cast<const float4*>(sB + c), b1 = *reinterpret_cast<const float4*>(sB + c + 4);
-        float o[8];
-        o[0] = (v[i][0] - mean) * rstd * a0.x + b0.x; o[1] = (v[i][1] - mean) * rstd * a0.y + b0.y;
-        o[2] = (v[i][2] - mean) * rstd * a0.z + b0.z; o[3] = (v[i][3] - mean) * rstd * a0.w + b0.w;
-        o[4] = (v[i][4] - mean) * rstd * a1.x + b1.x; o[5] = (v[i][5] - mean) * rstd * a1.y + b1.y;
-        o[6] = (v[i][6] - mean) * rstd * a1.z + b1.z; o[7] = (v[i][7] - mean) * rstd * a1.w + b1.w;
+        float v[8], o[8];
+        unpack8(raw[i], v);
+        o[0] = (v[0] - mean) * rstd * a0.x + b0.x; o[1] = (v[1] - mean) * rstd * a0.y + b0.y;
+        o[2] = (v[2] - mean) * rstd * a0.z + b0.z; o[3] = (v[3] - mean) * rstd * a0.w + b0.w;
+        o[4] = (v[4] - mean) * rstd * a1.x + b1.x; o[5] = (v[5] - mean) * rstd * a1.y + b1.y;
+        o[6] = (v[6] - mean) * rstd * a1.z + b1.z; o[7] = (v[7] - mean) * rstd * a1.w + b1.w;
         yr[i * 32 + lane] = pack8(o);
       }
     }
@@ -202,7 +212,7 @@ int ln_modulate(const void* x, void* y, int B, int S, int St, int D, const float
   auto xb = reinterpret_cast<const __nv_bfloat16*>(x);
   auto yb = reinterpret_cast<__nv_bfloat16*>(y);
   if (gamma2 == nullptr && rows >= 1024) {   // hot path: parameters staged in shared memory, persistent blocks
-    const int pgrid = num_sms() * 2;
+    const int pgrid = num_sms() * 2;          // two resident 8-warp blocks per SM (<= 128 registers per thread)
     const size_t smem = size_t(2) * D * sizeof(float);
 #define LAUNCH_S(V)                                                                                            \
   ln_modulate_smem_kernel<V><<<pgrid, 256, smem, stream>>>(xb, yb, B, S, St, gamma, beta, eps, shift_vid,      \
