@@ -27,6 +27,42 @@ def test_library_exports_every_declared_symbol():
     assert loaded.aether_abi_version() == 1
 
 
+def test_ctypes_signatures_match_header_prototypes():
+    """Every prototype of include/aether_b200.h against aether_b200/_lib.py::SIGNATURES: same number of parameters
+    and the same kind (pointer / 32-bit int / 64-bit int / float / double) in every position -- ctypes would
+    otherwise marshal a wrong call without any diagnostic."""
+    from aether_b200 import _lib
+    hdr = re.sub(r"/\*.*?\*/", " ", (ROOT / "include" / "aether_b200.h").read_text(), flags=re.S)
+    protos = re.findall(r"\b([A-Za-z_][A-Za-z0-9_ ]*?[\s\*])\s*(aether_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr)
+    assert len(protos) == len(_lib.SIGNATURES), (len(protos), len(_lib.SIGNATURES))
+
+    def kind_c(decl: str) -> str:
+        decl = decl.strip()
+        if "*" in decl:
+            return "ptr"
+        base = re.sub(r"\b(const|unsigned)\b", "", decl).split()
+        t = base[0] if base else ""
+        return {"int32_t": "i32", "int": "i32", "int64_t": "i64", "float": "f32", "double": "f64"}[t]
+
+    def kind_py(t) -> str:
+        if t is None:
+            return "void"
+        if t in (ctypes.c_void_p,) or (isinstance(t, type) and issubclass(t, ctypes._Pointer)):
+            return "ptr"
+        return {ctypes.c_int32: "i32", ctypes.c_int: "i32", ctypes.c_int64: "i64", ctypes.c_float: "f32",
+                ctypes.c_double: "f64"}[t]
+
+    for ret, name, params in protos:
+        res, args = _lib.SIGNATURES[name]
+        plist = [p for p in (x.strip() for x in params.split(",")) if p and p != "void"]
+        assert len(plist) == len(args), f"{name}: header has {len(plist)} parameters, ctypes binding {len(args)}"
+        for i, (pc, pa) in enumerate(zip(plist, args)):
+            assert kind_c(pc) == kind_py(pa), f"{name} parameter {i} ({pc!r}): header {kind_c(pc)}, binding {kind_py(pa)}"
+        ret = ret.strip()
+        want = "void" if ret == "void" else kind_c(ret)
+        assert want == kind_py(res), f"{name}: return type {ret!r} vs binding {res}"
+
+
 def test_library_has_no_libcuda_dependency():
     """The .so must load on a machine without the CUDA driver (driver entry points are resolved at run time)."""
     import subprocess
