@@ -73,7 +73,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Params p) {
   uint64_t* o_full = p_full + 2;            // [2]  MMA -> softmax  (last PV_t retired)
   uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(o_full + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform (see gemm_tcgen05.cu)
   const int lane = threadIdx.x & 31;
   const int q_blk = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int q0 = q_blk * 2 * BQ;
@@ -109,30 +109,42 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Params p) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_base_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_base_ptr, 0);
 
   if (warp < 4) {
     setmaxnreg_dec<48>();
-    if (warp == 0 && lane == 0) {
-      // ---------------------------------------------------------------- TMA producer
-      for (int t = 0; t < 2; ++t) {
-        mbar_arrive_expect_tx(&q_full[t], TILE_BYTES);
-        tma_load_4d(smem_q + t * TILE_BYTES, &tmap_qkv, &q_full[t], 0, h, q0 + t * BQ, b);
+    if (warp == 0) {
+      // ---------------------------------------------------------------- TMA producer (uniform control flow)
+      const bool lead = elect_one();
+      if (lead) {
+        for (int t = 0; t < 2; ++t) {
+          mbar_arrive_expect_tx(&q_full[t], TILE_BYTES);
+          tma_load_4d(smem_q + t * TILE_BYTES, &tmap_qkv, &q_full[t], 0, h, q0 + t * BQ, b);
+        }
       }
+      __syncwarp();
       int ks = 0, vs = 0;
       uint32_t kph = 0, vph = 0;
       for (int j = 0; j < n_kv; ++j) {
         mbar_wait(&k_empty[ks], kph ^ 1);
-        mbar_arrive_expect_tx(&k_full[ks], TILE_BYTES);
-        tma_load_4d(smem_k + ks * TILE_BYTES, &tmap_qkv, &k_full[ks], 0, H + h, j * BKV, b);
+        if (lead) {
+          mbar_arrive_expect_tx(&k_full[ks], TILE_BYTES);
+          tma_load_4d(smem_k + ks * TILE_BYTES, &tmap_qkv, &k_full[ks], 0, H + h, j * BKV, b);
+        }
+        __syncwarp();
         if (++ks == KSTAGES) { ks = 0; kph ^= 1; }
         mbar_wait(&v_empty[vs], vph ^ 1);
-        mbar_arrive_expect_tx(&v_full[vs], TILE_BYTES);
-        tma_load_4d(smem_v + vs * TILE_BYTES, &tmap_qkv, &v_full[vs], 0, 2 * H + h, j * BKV, b);
+        if (lead) {
+          mbar_arrive_expect_tx(&v_full[vs], TILE_BYTES);
+          tma_load_4d(smem_v + vs * TILE_BYTES, &tmap_qkv, &v_full[vs], 0, 2 * H + h, j * BKV, b);
+        }
+        __syncwarp();
         if (++vs == VSTAGES) { vs = 0; vph ^= 1; }
       }
-    } else if (warp == 1 && lane == 0) {
-      // ---------------------------------------------------------------- MMA issuer
+    } else if (warp == 1) {
+      // ---------------------------------------------------------------- MMA issuer: the whole warp walks the schedule
+      // (uniform control flow -> back-to-back UTCHMMA, see gemm_tcgen05.cu), one elected lane issues.
+      const bool lead = elect_one();
       constexpr uint32_t PV_FMT = F16PV ? 0u : 1u;                                      // 0 = F16, 1 = BF16
       constexpr uint32_t idesc_qk = make_idesc_f16kind(BQ, BKV, 1, 1, 0, 0);            // Q, K bf16, both K-major
       constexpr uint32_t idesc_pv = make_idesc_f16kind(BQ, DH, PV_FMT, PV_FMT, 0, 1);   // P (TMEM), V MN-major
@@ -165,13 +177,19 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Params p) {
       mbar_wait(&k_full[0], 0);
       mbar_wait(&q_full[0], 0);
       tc_fence_after();
-      issue_qk(0, 0);
-      tc_commit(&s_full[0]);
+      if (lead) {
+        issue_qk(0, 0);
+        tc_commit(&s_full[0]);
+      }
+      __syncwarp();
       mbar_wait(&q_full[1], 0);
       tc_fence_after();
-      issue_qk(1, 0);
-      tc_commit(&s_full[1]);
-      tc_commit(&k_empty[0]);
+      if (lead) {
+        issue_qk(1, 0);
+        tc_commit(&s_full[1]);
+        tc_commit(&k_empty[0]);
+      }
+      __syncwarp();
       ks = 1;
       if (ks == KSTAGES) { ks = 0; kph ^= 1; }
       for (int j = 0; j < n_kv; ++j) {
@@ -180,27 +198,36 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Params p) {
         // ---- tile 0
         mbar_wait(&p_full[0], pph);
         tc_fence_after();
-        issue_pv(0, vs, j == 0);
+        if (lead) issue_pv(0, vs, j == 0);
+        __syncwarp();
         if (!last) {
           mbar_wait(&k_full[ks], kph);
           tc_fence_after();
-          issue_qk(0, ks);
-          tc_commit(&s_full[0]);
+          if (lead) {
+            issue_qk(0, ks);
+            tc_commit(&s_full[0]);
+          }
         } else {
-          tc_commit(&o_full[0]);
+          if (lead) tc_commit(&o_full[0]);
         }
+        __syncwarp();
         // ---- tile 1
         mbar_wait(&p_full[1], pph);
         tc_fence_after();
-        issue_pv(1, vs, j == 0);
-        tc_commit(&v_empty[vs]);
+        if (lead) {
+          issue_pv(1, vs, j == 0);
+          tc_commit(&v_empty[vs]);
+          if (!last) {
+            issue_qk(1, ks);
+            tc_commit(&s_full[1]);
+            tc_commit(&k_empty[ks]);
+          } else {
+            tc_commit(&o_full[1]);
+          }
+        }
+        __syncwarp();
         if (!last) {
-          issue_qk(1, ks);
-          tc_commit(&s_full[1]);
-          tc_commit(&k_empty[ks]);
           if (++ks == KSTAGES) { ks = 0; kph ^= 1; }
-        } else {
-          tc_commit(&o_full[1]);
         }
         if (++vs == VSTAGES) { vs = 0; vph ^= 1; }
         pph ^= 1;
