@@ -1,14 +1,15 @@
 // K1, variant 3 (mode 5 of aether_attention_bf16): decoupled S / P buffers.
 //
-// Measurement-driven redesign of attention_tcgen05.cu (mode 0).  On B200 the TMEM -> register path (tcgen05.ld)
-// moves ~64 B/clk/SM = 16 fp32 scores per clock (mode 3, which reads S twice, costs +1315 clk per extra 64 KB) and
-// the MUFU computes 16 ex2 per clock: BOTH pipes need 1024 clk per 128x128 score tile, against 512 clk of tensor
-// work (dh = 64).  In mode 0 P aliases S, so S_t(j+1) can only be produced after PV_t(j): every softmax warpgroup
-// idles for a full MMA round trip (~700 clk) per key tile.  Here P gets its own TMEM columns
+// Measurement-driven redesign of attention_tcgen05.cu (mode 0).  At head_dim 64 the MUFU (16 ex2 per clock per SM) needs
+// 1024 clk per 128x128 score tile against 512 clk of tensor work, so the softmax warps must never wait for the MMA
+// warp.  (This header first also blamed the TMEM -> register path; the ncu counter smsp__mem_tensor_reads_op_ldt later
+// showed tcgen05.ld at 5 % of its bandwidth -- see DESIGN.md "Attention roofline".)  In mode 0 P aliases S, so
+// S_t(j+1) can only be produced after PV_t(j): every softmax warpgroup idles for a full MMA round trip per key tile.
+// Here P gets its own TMEM columns
 //     S0 [0,128)  S1 [128,256)  P0 [256,320)  P1 [320,384)  O0 [384,448)  O1 [448,512)      (all 512 columns)
 // and the softmax warps release S_t as soon as it sits in registers (s_free), so the MMA warp issues QK_t(j+1)
-// DURING the exp phase of tile t.  Per warpgroup the steady state is  load S (LDTM-bound) -> exp/pack/store
-// (MUFU-bound) with no MMA wait; the two warpgroups run in anti-phase, one on each pipe.
+// DURING the exp phase of tile t.  Per warpgroup the steady state is  load S -> row max -> exp/pack/store
+// (MUFU-bound) with no MMA wait; the issue order below starts the two warpgroups half a period apart.
 //   MMA issue order per key tile j:  QK_0(j+1) | PV_0(j) | QK_1(j+1) | PV_1(j)
 //   barriers:  s_full (MMA->softmax)  s_free (softmax->MMA, 128 arrivals)  p_full (softmax->MMA, 128)
 //              p_free (MMA->softmax: PV_t(j) retired => P_t and O_t may be touched again)  o_full (last PV retired)

@@ -1,11 +1,11 @@
 // K1, variant 5 (mode 8 of aether_attention_bf16): 64-key tiles, S double-buffered per query tile, and every softmax
 // warp keeps the tcgen05.ld of S(j+1) IN FLIGHT while it runs the exponentials of S(j).
 //
-// Why: at head_dim 64 both the TMEM->register path (64 B/clk/SM) and the MUFU (16 ex2/clk/SM) need 1024 clk per
-// 128x128 scores, the tensor pipe only 512.  Mode 5 loads a whole 128-column tile, waits, then runs the MUFU phase;
-// its two warpgroups were meant to alternate pipes but measure 1530 clk per tile (MUFU 67 % busy).  Here the two
-// pipes overlap INSIDE each warp -- the load of the next 64 columns is asynchronous and retires during ~512 clk of
-// exponentials -- and the second warp of each scheduler fills the remaining max / pack / store gaps.
+// Why (hypothesis at the time): the MUFU (16 ex2/clk/SM) needs 1024 clk per 128x128 scores, the tensor pipe 512; mode
+// 5 loads a whole 128-column tile, waits, then runs the MUFU phase and measured 1530 clk per tile (MUFU 67 % busy).
+// Here the S load of the next 64 columns is asynchronous and retires during the exponentials, and S / P are
+// double-buffered so the MMA warp can run two key tiles ahead.  Outcome: correct, 3.74 ms -- the real limiter of
+// mode 5 was the MMA-issue waterfall, not the load; kept as a variant (mode 8).
 //
 // TMEM (512 columns), per query tile t in {0,1} at base t*256:
 //     S_t[0] +0   S_t[1] +64   P_t[0] +128 (32 cols, bf16)   P_t[1] +160   O_t +192 (64 cols)
