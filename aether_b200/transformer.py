@@ -130,7 +130,8 @@ class AetherTransformer3D(nn.Module):
         self._n_layers_override = -1
         # kernel-mode switch (not a model hyper-parameter), set before pack(): attention kernel variant 0..12
         # (csrc/attention*_tcgen05.cu, DESIGN.md "Attention roofline"); 5 = decoupled S/P buffers + skewed MMA
-        # schedule, measured fastest (3.30 ms at S=15076).  AETHER_ATTENTION_MODE overrides it for A/B timing.
+        # schedule, 3.31 ms at S=15076 and the fastest variant timed inside the step (mode 2, fp16 P/V, is 3.21 ms
+        # isolated but has not been A/B-timed in the power-capped step).  AETHER_ATTENTION_MODE overrides it.
         import os
         self.attention_fp16_pv = int(os.environ.get("AETHER_ATTENTION_MODE", "5"))
 
