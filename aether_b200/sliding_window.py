@@ -237,3 +237,34 @@ def process_with_sliding_window(pipeline, obs_image: np.ndarray, num_inference_s
         dist.broadcast(r, src=0, group=group)
         rgb0 = r.cpu().numpy()
     return np.asarray(rgb0), final.cpu().numpy()
+
+
+# ------------------------------------------------------------------------------------------ launcher glue (host side)
+def prepare_frames(images: Sequence[np.ndarray]) -> np.ndarray:
+    """`prepare_input` of launch_aether.py:388-403 without the file read: every H x W x 3 uint8 frame is resized so
+    that the short side of the 480 x 720 window is met exactly (aspect kept, `cv2.resize` default = bilinear) and
+    scaled to [0, 1] float64.  Returns [T, new_h, new_w, 3]."""
+    import cv2  # the reference's resampler; there is no substitute that reproduces its rounding
+    out = []
+    for img in images:
+        h, w = img.shape[:2]
+        aspect_ratio = w / h
+        new_h, new_w = ((480, int(round(480 * aspect_ratio))) if aspect_ratio > 720 / 480
+                        else (int(round(720 / aspect_ratio)), 720))
+        out.append(cv2.resize(img, (new_w, new_h)) / 255.0)
+    return np.stack(out)
+
+
+def disparity_to_depth(disparity: np.ndarray) -> np.ndarray:
+    """launch_aether.py:347: depth_maps = np.clip(1.0 / disparity_video, 0, 1e2)."""
+    return np.clip(1.0 / disparity, 0, 1e2)
+
+
+def evaluate_sequence(pipeline, frames: Sequence[np.ndarray], num_inference_step: int, seed: int, rank: int = 0,
+                      world_size: int = 1, group=None, device: Optional[torch.device] = None):
+    """One sequence of the video-depth evaluation (launch_aether.py:338-347) with the tiles spread over `world_size`
+    ranks: frames -> prepare_frames -> sliding-window inference + blend -> (rgb of tile 0, disparity, depth)."""
+    obs = prepare_frames(frames)[None]
+    rgb, disparity = process_with_sliding_window(pipeline, obs, num_inference_step, len(frames), seed, rank=rank,
+                                                 world_size=world_size, group=group, device=device)
+    return rgb, disparity, disparity_to_depth(disparity)

@@ -193,9 +193,28 @@ def make_pipeline():
     print("pipeline_errors.npz", msgs)
 
 
+def make_prepare_input():
+    from helpers import PREPARE_INPUT_SIZES, prepare_input_frames
+    """launch_aether.py:388-403 prepare_input (aspect-preserving cv2 resize to the 480 x 720 window, /255) on seeded
+    uint8 frames; the file read is replaced by a lookup."""
+    EVD = shim.reference_sliding_window_module()
+    out = {}
+    for h, w in PREPARE_INPUT_SIZES:
+        frames = prepare_input_frames(h, w)
+        EVD.iio.imread = lambda p, frames=frames: frames[int(p)]
+        ref = EVD.prepare_input([str(i) for i in range(len(frames))])
+        out[f"{h}x{w}__shape"] = np.array(ref.shape)
+        out[f"{h}x{w}__sum"] = np.float64(ref.sum())
+        out[f"{h}x{w}__sub"] = subsample(ref, (1, 24, 24, 1))
+    np.savez_compressed(HERE / "prepare_input.npz", **out)
+    print("prepare_input.npz", len(out))
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
-    which = sys.argv[1:] or ["rope", "scale", "sliding", "pipeline"]
+    which = sys.argv[1:] or ["rope", "scale", "sliding", "pipeline", "prepare"]
+    if "prepare" in which:
+        make_prepare_input()
     if "rope" in which:
         make_rope()
     if "scale" in which:

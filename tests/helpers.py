@@ -76,3 +76,12 @@ def synthetic_long_clip(t, h, w, seed=11) -> np.ndarray:
 def subsample(a: np.ndarray, steps) -> np.ndarray:
     sl = tuple(slice(None, None, s) for s in steps)
     return np.ascontiguousarray(a[sl])
+
+
+PREPARE_INPUT_SIZES = [(720, 1280), (436, 1024), (480, 640), (1080, 1920), (600, 600)]
+
+
+def prepare_input_frames(h, w, n=2):
+    """Seeded uint8 frames for the prepare_input golden (tests/golden/make_golden.py::make_prepare_input)."""
+    g = np.random.default_rng(h * 10000 + w)
+    return [g.integers(0, 256, size=(h, w, 3), dtype=np.uint8) for _ in range(n)]

@@ -106,6 +106,24 @@ def test_tile_plan_and_blend_match_reference(golden_dir, name):
     assert final.sum() == pytest.approx(float(g["disparity_sum"]), rel=1e-12)
 
 
+def test_prepare_frames_and_depth_match_reference_launcher(golden_dir):
+    """Launcher glue either side of the tile loop: `prepare_input` (launch_aether.py:388-403) against the golden made
+    by the reference's own function, and depth = clip(1 / disparity, 0, 100) (:347)."""
+    pytest.importorskip("cv2")
+    from aether_b200.sliding_window import disparity_to_depth, plan_windows, prepare_frames
+    from helpers import PREPARE_INPUT_SIZES, prepare_input_frames
+    g = np.load(golden_dir / "prepare_input.npz")
+    for h, w in PREPARE_INPUT_SIZES:
+        got = prepare_frames(prepare_input_frames(h, w))
+        assert got.dtype == np.float64 and list(got.shape) == g[f"{h}x{w}__shape"].tolist()
+        assert got.sum() == float(g[f"{h}x{w}__sum"])
+        assert np.array_equal(subsample(got, (1, 24, 24, 1)), g[f"{h}x{w}__sub"])
+        plan_windows(got.shape[0], got.shape[1], got.shape[2])          # always a single tiling direction
+    d = np.array([[0.0, 1e-3, 0.5, 4.0]])
+    with np.errstate(divide="ignore"):
+        assert np.array_equal(disparity_to_depth(d), np.array([[100.0, 100.0, 2.0, 0.25]]))
+
+
 def test_plan_config5_geometry():
     """512 frames of 480x853 -> 60 temporal x 2 spatial = 120 tiles, overlap 587 px."""
     from aether_b200.sliding_window import partition_tiles, plan_windows
