@@ -191,6 +191,10 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const CUtensorMap
         }
       }
       if (n >= p.f16_from) {
+        // fp16 columns (V of the fp16-P/V attention variants): saturate instead of overflowing to inf -- bf16, which
+        // the reference keeps V in, has fp32's range (NaN still propagates: both comparisons are false for it)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = x[j] > 65504.f ? 65504.f : (x[j] < -65504.f ? -65504.f : x[j]);
 #pragma unroll
         for (int j = 0; j < 4; ++j) packed[g8 * 4 + j] = pack_f16x2(x[2 * j], x[2 * j + 1]);
       } else {
