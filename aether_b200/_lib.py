@@ -23,7 +23,7 @@ class DitConfig(C.Structure):
                 ("in_channels", c_int32), ("out_channels", c_int32), ("patch_size", c_int32),
                 ("time_embed_dim", c_int32), ("text_embed_dim", c_int32), ("flip_sin_to_cos", c_int32),
                 ("freq_shift", c_float), ("norm_eps", c_float), ("ff_mult", c_int32),
-                ("attention_fp16_pv", c_int32)]
+                ("attention_fp16_pv", c_int32), ("fused_qkv_epilogue", c_int32)]
 
 
 class DitLayerWeights(C.Structure):
@@ -142,6 +142,46 @@ def ptr(t) -> int:
 def current_stream() -> int:
     import torch
     return torch.cuda.current_stream().cuda_stream
+
+
+def _cuda_tensors(obj, found):
+    import torch
+    if isinstance(obj, torch.Tensor):
+        if obj.is_cuda:
+            found.append(obj)
+    elif isinstance(obj, (list, tuple)):
+        for o in obj:
+            _cuda_tensors(o, found)
+
+
+def device_guard(fn):
+    """Run `fn` with the CUDA device of its tensor arguments current.
+
+    The C ABI takes raw device pointers plus a stream handle; `torch.cuda.current_stream()` and the kernels' launch
+    context follow the CURRENT device, not the tensors' device.  This decorator makes every entry point safe for
+    `module.to("cuda:1")` without `torch.cuda.set_device(1)`: it checks that all CUDA tensor arguments live on one
+    device and switches to it for the duration of the call.  A bound method whose object exposes a CUDA `.device`
+    (packed module) contributes that device too."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        import torch
+        found = []
+        _cuda_tensors(args, found)
+        _cuda_tensors(tuple(kwargs.values()), found)
+        devs = {t.device for t in found}
+        if args and not isinstance(args[0], torch.Tensor):
+            d = getattr(args[0], "device", None)
+            if isinstance(d, torch.device) and d.type == "cuda":
+                devs.add(d if d.index is not None else torch.device("cuda", torch.cuda.current_device()))
+        if len(devs) > 1:
+            raise ValueError(f"{fn.__qualname__}: tensors live on different CUDA devices: {sorted(map(str, devs))}")
+        if not devs:
+            return fn(*args, **kwargs)
+        with torch.cuda.device(next(iter(devs))):
+            return fn(*args, **kwargs)
+    return wrapper
 
 
 def require_device():

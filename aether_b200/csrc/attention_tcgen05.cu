@@ -456,12 +456,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Params p) {
 
 template <int MODE>
 static int launch(const CUtensorMap& tm, const Params& p, dim3 grid, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    AETHER_CUDA_OK(cudaFuncSetAttribute(attention_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        SMEM_BYTES));
-    attr_set = true;
-  }
+  static SmemGrant grant;
+  AETHER_CUDA_OK(ensure_dynamic_smem(grant, attention_kernel<MODE>, SMEM_BYTES));
   attention_kernel<MODE><<<grid, THREADS, SMEM_BYTES, stream>>>(tm, p);
   AETHER_CUDA_OK(cudaGetLastError());
   return AETHER_OK;

@@ -269,12 +269,8 @@ attention_v2_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Params p
 }  // namespace attn2
 
 int attention_v2_launch(const CUtensorMap& tm, int B, int S, int H, void* out, float scale_log2, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    AETHER_CUDA_OK(cudaFuncSetAttribute(attn2::attention_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        attn2::SMEM_BYTES));
-    attr_set = true;
-  }
+  static SmemGrant grant;
+  AETHER_CUDA_OK(ensure_dynamic_smem(grant, attn2::attention_v2_kernel, attn2::SMEM_BYTES));
   attn2::Params p;
   p.B = B; p.H = H; p.S = S;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);

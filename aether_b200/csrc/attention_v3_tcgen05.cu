@@ -520,13 +520,9 @@ int attention_v3_launch_blocks(const CUtensorMap& tm, int B, int S, int H, void*
   static const Kernel kernels[6] = {attn3::attention_v3_kernel<false, 0>, attn3::attention_v3_kernel<true, 0>,
                                     attn3::attention_v3_kernel<false, 0x88>, attn3::attention_v3_kernel<false, 0x80>,
                                     attn3::attention_v3_kernel<false, 0xA4>, attn3::attention_v3_kernel<false, -1>};
-  static bool attr_set = false;
-  if (!attr_set) {
-    for (Kernel k : kernels)
-      AETHER_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, attn3::SMEM_BYTES));
-    attr_set = true;
-  }
   AETHER_CHECK_ARG(variant >= 0 && variant < 6);
+  static SmemGrant grants[6];
+  AETHER_CUDA_OK(ensure_dynamic_smem(grants[variant], kernels[variant], attn3::SMEM_BYTES));
   attn3::Params p;
   p.B = B; p.H = H; p.S = S;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);

@@ -303,12 +303,8 @@ int attention_v4_launch(const CUtensorMap& tm, int B, int S, int H, void* out, f
 // Query rows [q_row0, S) only (all keys): the tail launch of the split mode-5 schedule.
 int attention_v4_launch_rows(const CUtensorMap& tm, int B, int S, int H, void* out, float scale_log2, int q_row0,
                              cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    AETHER_CUDA_OK(cudaFuncSetAttribute(attn4::attention_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        attn4::SMEM_BYTES));
-    attr_set = true;
-  }
+  static SmemGrant grant;
+  AETHER_CUDA_OK(ensure_dynamic_smem(grant, attn4::attention_v4_kernel, attn4::SMEM_BYTES));
   attn4::Params p;
   p.B = B; p.H = H; p.S = S;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);

@@ -316,12 +316,8 @@ attention_v6_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Params p
 }  // namespace attn6
 
 int attention_v6_launch(const void* qkv, int B, int S, int H, void* out, float scale_log2, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    AETHER_CUDA_OK(cudaFuncSetAttribute(attn6::attention_v6_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        attn6::SMEM_BYTES));
-    attr_set = true;
-  }
+  static SmemGrant grant;
+  AETHER_CUDA_OK(ensure_dynamic_smem(grant, attn6::attention_v6_kernel, attn6::SMEM_BYTES));
   CUtensorMap tm;
   const uint64_t dims[4] = {64, uint64_t(3 * H), uint64_t(S), uint64_t(B)};
   const uint64_t strides[3] = {128, uint64_t(3 * H) * 128, uint64_t(S) * uint64_t(3 * H) * 128};

@@ -265,12 +265,8 @@ conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
 
 template <int BN>
 int launch(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, const Params& p, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    AETHER_CUDA_OK(cudaFuncSetAttribute(conv_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        Cfg<BN>::SMEM_BYTES));
-    attr_set = true;
-  }
+  static SmemGrant grant;
+  AETHER_CUDA_OK(ensure_dynamic_smem(grant, conv_kernel<BN>, Cfg<BN>::SMEM_BYTES));
   const int64_t tiles = int64_t(p.T) * p.tiles_y * p.tiles_x * p.num_n;
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
   conv_kernel<BN><<<grid, THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(tx, tw, ty, p);

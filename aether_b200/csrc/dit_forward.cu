@@ -220,14 +220,11 @@ static int dit_forward_impl(AetherDit* h, const void* in0, int C0, int B0, const
   // ---- transformer blocks
   const int run_layers = (n_layers < 0 || n_layers > L) ? L : n_layers;
   const float softmax_scale = 1.0f / sqrtf(float(c.head_dim));
-  // AETHER_FUSED_QK=1 runs QK-LayerNorm + RoPE inside the QKV GEMM epilogue (aether_gemm_qkv_norm_rope_bf16).  Measured
-  // on B200 at S = 15076: 267.7 ms/step fused vs 264.5 ms with the separate qk_norm_rope launch -- four epilogue warps
-  // doing 64-wide LayerNorms with row-private cos/sin loads take longer than the 24.5k-clk main loop that should hide
-  // them, so the separate HBM-bound kernel (0.12 ms) stays the default until the epilogue runs on eight warps.
-  static const bool fused_qk = [] {
-    const char* e = getenv("AETHER_FUSED_QK");
-    return e != nullptr && e[0] == '1';
-  }();
+  // cfg.fused_qkv_epilogue = 1 runs QK-LayerNorm + RoPE inside the QKV GEMM epilogue (aether_gemm_qkv_norm_rope_bf16).
+  // Measured on B200 at S = 15076: 267.7 ms/step fused vs 264.5 ms with the separate qk_norm_rope launch -- four
+  // epilogue warps doing 64-wide LayerNorms with row-private cos/sin loads take longer than the 24.5k-clk main loop
+  // that should hide them, so the separate HBM-bound kernel (0.12 ms) stays the default.
+  const bool fused_qk = c.fused_qkv_epilogue != 0;
   for (int l = 0; l < run_layers; ++l) {
     const AetherDitLayerWeights& lw = h->layers[l];
     // CogVideoXLayerNormZero chunk order: shift, scale, gate, enc_shift, enc_scale, enc_gate

@@ -529,11 +529,8 @@ int patchify2(const void* in0, int C0, int B0, const void* in1, int C1, void* pa
   AETHER_CHECK_ARG(B0 == 1 || B0 == B);
   const size_t smem = size_t(2) * C * (W / 2) * 4;
   AETHER_CHECK_ARG(smem <= 160 * 1024);
-  static size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
-    AETHER_CUDA_OK(cudaFuncSetAttribute(patchify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
-  }
+  static SmemGrant grant;
+  AETHER_CUDA_OK(ensure_dynamic_smem(grant, patchify_kernel, smem));
   patchify_kernel<<<(unsigned)(B * F * (H / 2)), 256, smem, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(in0), C0, B0, reinterpret_cast<const __nv_bfloat16*>(in1), C1,
       reinterpret_cast<__nv_bfloat16*>(patches), F, H, W);
@@ -572,11 +569,8 @@ int unpatchify(const void* tok, int64_t ld_tok, void* out, int B, int F, int C, 
   AETHER_CHECK_ARG(B > 0 && F > 0 && C > 0 && H % 2 == 0 && W % 2 == 0 && ld_tok % 2 == 0 && ld_tok >= 4 * C);
   const size_t smem = size_t(2) * C * (W / 2) * 4;
   AETHER_CHECK_ARG(smem <= 160 * 1024);
-  static size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
-    AETHER_CUDA_OK(cudaFuncSetAttribute(unpatchify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
-  }
+  static SmemGrant grant;
+  AETHER_CUDA_OK(ensure_dynamic_smem(grant, unpatchify_kernel, smem));
   unpatchify_kernel<<<(unsigned)(B * F * (H / 2)), 256, smem, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(tok), ld_tok, reinterpret_cast<__nv_bfloat16*>(out), C, H, W);
   AETHER_CUDA_OK(cudaGetLastError());

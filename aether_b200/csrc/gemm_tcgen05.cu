@@ -520,11 +520,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
 
 template <int EPI>
 int launch2(const CUtensorMap& ta, const CUtensorMap& tbh, const CUtensorMap& tc, const Params& p, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    AETHER_CUDA_OK(cudaFuncSetAttribute(gemm2_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
-    attr_set = true;
-  }
+  static SmemGrant grant;
+  AETHER_CUDA_OK(ensure_dynamic_smem(grant, gemm2_kernel<EPI>, SMEM2_BYTES));
   const int tiles = p.num_m * p.num_n;
   const int pairs = num_sms() / 2;
   const int grid = 2 * (tiles < pairs ? tiles : pairs);
@@ -535,11 +532,8 @@ int launch2(const CUtensorMap& ta, const CUtensorMap& tbh, const CUtensorMap& tc
 
 template <int EPI>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const Params& p, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    AETHER_CUDA_OK(cudaFuncSetAttribute(gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
-  }
+  static SmemGrant grant;
+  AETHER_CUDA_OK(ensure_dynamic_smem(grant, gemm_kernel<EPI>, SMEM_BYTES));
   const int tiles = p.num_m * p.num_n;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   gemm_kernel<EPI><<<grid, THREADS, SMEM_BYTES, stream>>>(ta, tb, tc, p);
@@ -581,12 +575,8 @@ static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, voi
     p.qn_g = qk->qn_g; p.qn_b = qk->qn_b; p.kn_g = qk->kn_g; p.kn_b = qk->kn_b;
     p.rope_cos = qk->rope_cos; p.rope_sin = qk->rope_sin; p.qk_eps = qk->qk_eps; p.heads = qk->heads;
   }
-  // Large problems run on CTA pairs (cta_group::2); AETHER_GEMM_1CTA=1 forces the single-CTA kernel for A/B timing.
-  static const bool force_1cta = [] {
-    const char* e = getenv("AETHER_GEMM_1CTA");
-    return e != nullptr && e[0] == '1';
-  }();
-  if (!force_1cta && M >= 1024 && N >= gemm::BN && num_sms() >= 2) {
+  // Large problems run on CTA pairs (cta_group::2).
+  if (M >= 1024 && N >= gemm::BN && num_sms() >= 2) {
     CUtensorMap tbh;
     if ((rc = make_tmap_2d(&tbh, W, N, K, ldw, gemm::BN / 2, gemm::BK))) return rc;
     gemm::Params p2 = p;

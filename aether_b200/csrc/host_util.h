@@ -7,6 +7,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/aether_b200.h"
 
 namespace aether {
@@ -87,13 +89,41 @@ inline int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint6
   return make_tmap_bf16(out, base, 2, dims, str, box, true);
 }
 
-inline int num_sms() {
-  static int n = 0;
-  if (n) return n;
+constexpr int kMaxDevices = 64;
+
+inline int current_device() {
   int dev = 0;
   cudaGetDevice(&dev);
+  return dev;
+}
+
+// SM count of the CURRENT device (the one the caller's stream belongs to), cached per device ordinal.
+inline int num_sms() {
+  static std::atomic<int> cache[kMaxDevices];
+  const int dev = current_device();
+  std::atomic<int>* slot = (dev >= 0 && dev < kMaxDevices) ? &cache[dev] : nullptr;
+  int n = slot ? slot->load(std::memory_order_relaxed) : 0;
+  if (n) return n;
   cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  if (slot) slot->store(n, std::memory_order_relaxed);
   return n;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE property of a kernel: remember, per launcher and per
+// device ordinal, the size already granted.  Re-entrant (two threads may both set the same value; that is idempotent).
+struct SmemGrant {
+  std::atomic<int> bytes[kMaxDevices];
+};
+
+template <typename KernelT>
+inline cudaError_t ensure_dynamic_smem(SmemGrant& g, KernelT kernel, size_t bytes) {
+  if (bytes <= 48 * 1024) return cudaSuccess;
+  const int dev = current_device();
+  std::atomic<int>* slot = (dev >= 0 && dev < kMaxDevices) ? &g.bytes[dev] : nullptr;
+  if (slot && slot->load(std::memory_order_acquire) >= (int)bytes) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess && slot) slot->store((int)bytes, std::memory_order_release);
+  return e;
 }
 
 }  // namespace aether

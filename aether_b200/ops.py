@@ -12,7 +12,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import check, current_stream, ptr
+from ._lib import check, current_stream, device_guard, ptr
 
 BF16, F32, F64 = torch.bfloat16, torch.float32, torch.float64
 
@@ -23,6 +23,7 @@ def _need(t: torch.Tensor, dtype, name: str):
                          f"contiguous={t.is_contiguous()}")
 
 
+@device_guard
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, epilogue: int = 0,
          out: Optional[torch.Tensor] = None, gate_vid=None, gate_txt=None, S: int = 0, St: int = 0,
          f16_from_col: int = -1) -> torch.Tensor:
@@ -47,6 +48,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     return out
 
 
+@device_guard
 def attention(qkv: torch.Tensor, scale: Optional[float] = None, v_fp16: bool = False) -> torch.Tensor:
     """qkv [B,S,3,H,64] bf16 -> out [B,S,H*64] bf16.  With v_fp16 the V third holds fp16 bit patterns
     (`qkv.view(torch.float16)[:, :, 2] = v.half()`) and the fp16-PV kernel mode runs."""
@@ -60,6 +62,7 @@ def attention(qkv: torch.Tensor, scale: Optional[float] = None, v_fp16: bool = F
     return out
 
 
+@device_guard
 def ln_modulate(x, gamma, beta, eps, shift_vid, scale_vid, shift_txt=None, scale_txt=None, St=0, gamma2=None,
                 beta2=None, mod_bstride=None, out=None):
     """x [B,S,D] bf16; shift/scale fp32 [B,D] (or views with batch stride mod_bstride)."""
@@ -76,6 +79,7 @@ def ln_modulate(x, gamma, beta, eps, shift_vid, scale_vid, shift_txt=None, scale
     return out
 
 
+@device_guard
 def qk_norm_rope(qkv, gq, bq, gk, bk, eps=1e-6, cos=None, sin=None, St=0):
     lib = _lib.require_device()
     _need(qkv, BF16, "qkv")
@@ -90,6 +94,7 @@ def qk_norm_rope(qkv, gq, bq, gk, bk, eps=1e-6, cos=None, sin=None, St=0):
     return qkv
 
 
+@device_guard
 def gemm_qkv_norm_rope(x, w, bias, B, S, St, H, gq, bq, gk, bk, eps=1e-6, cos=None, sin=None, f16_from_col=-1):
     """x [B*S, K] bf16, w [3*H*64, K] bf16 -> qkv [B, S, 3, H, 64] bf16 with q / k already QK-LayerNorm'ed and rotated
     (the fused epilogue of the QKV projection; same values as gemm(...) followed by qk_norm_rope(...))."""
@@ -111,6 +116,7 @@ def gemm_qkv_norm_rope(x, w, bias, B, S, St, H, gq, bq, gk, bk, eps=1e-6, cos=No
     return qkv
 
 
+@device_guard
 def small_m_linear(x, w, bias=None, act=0):
     lib = _lib.require_device()
     _need(x, F32, "x"); _need(w, BF16, "w")
@@ -122,6 +128,7 @@ def small_m_linear(x, w, bias=None, act=0):
     return y
 
 
+@device_guard
 def timestep_sinusoid(t, dim, flip_sin_to_cos=True, freq_shift=0.0):
     lib = _lib.require_device()
     _need(t, torch.int64, "timesteps")
@@ -131,6 +138,7 @@ def timestep_sinusoid(t, dim, flip_sin_to_cos=True, freq_shift=0.0):
     return emb
 
 
+@device_guard
 def patchify(x):
     lib = _lib.require_device()
     _need(x, BF16, "x")
@@ -140,6 +148,7 @@ def patchify(x):
     return out
 
 
+@device_guard
 def unpatchify(tok, B, F, Cc, H, W):
     lib = _lib.require_device()
     _need(tok, BF16, "tok")
@@ -154,6 +163,7 @@ def dpm_coeffs(sqrt_alpha, sqrt_one_minus_alpha, m1, m2, m3, m4, m_noise, second
                           int(second_order), int(prediction_type))
 
 
+@device_guard
 def cfg_dpm_step(model_out, sample, coeffs, noise1, noise2=None, old_x0=None, guidance=1.0, want_prev_f32=False):
     """model_out [n_cfg, ...] bf16 or fp32; sample bf16 -> (prev_bf16, prev_f32 | None, x0_f32)."""
     lib = _lib.require_device()

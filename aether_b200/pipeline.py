@@ -478,6 +478,9 @@ class AetherV1PipelineCogVideoX:
         n_cfg = 2 if do_cfg else 1
         text = prompt_embeds.repeat(n_cfg, 1, 1)
         fused = hasattr(self.scheduler, "step_fused")
+        # the reference dispatches on isinstance(scheduler, CogVideoXDPMScheduler) (:902); without diffusers the same
+        # decision is taken on the capability that class adds: the `old_pred_original_sample` / `timestep_back` arguments
+        dpm_signature = "old_pred_original_sample" in inspect.signature(self.scheduler.step).parameters
         # with the aether_b200 transformer the concat / repeat / expand of :832-869 happen inside the patch-gather
         # kernel (aether_dit_forward_split): the loop body is then exactly two C-ABI calls
         split = fused and hasattr(self.transformer, "forward_split") and ofs_emb is None
@@ -515,9 +518,13 @@ class AetherV1PipelineCogVideoX:
                     if do_cfg:
                         nu, ntxt = noise_pred.chunk(2)
                         noise_pred = nu + self.guidance_scale * (ntxt - nu)
-                    latents, old_pred_original_sample = self.scheduler.step(
-                        noise_pred, old_pred_original_sample, t, t_back, latents, **extra_step_kwargs,
-                        return_dict=False)
+                    if dpm_signature:     # reference :902-915: CogVideoXDPMScheduler vs. DDIM-style signature
+                        latents, old_pred_original_sample = self.scheduler.step(
+                            noise_pred, old_pred_original_sample, t, t_back, latents, **extra_step_kwargs,
+                            return_dict=False)
+                    else:
+                        latents = self.scheduler.step(noise_pred, t, latents, **extra_step_kwargs,
+                                                      return_dict=False)[0]
                     latents = latents.to(prompt_embeds.dtype)
                 if i == len(timesteps) - 1 or ((i + 1) > num_warmup_steps and (i + 1) % self.scheduler.order == 0):
                     progress_bar.update()

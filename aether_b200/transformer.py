@@ -26,7 +26,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from ._lib import DitConfig, DitLayerWeights, DitWeights, check, current_stream, ptr
+from ._lib import DitConfig, DitLayerWeights, DitWeights, check, current_stream, device_guard, ptr
 
 _DEFAULTS = dict(
     num_attention_heads=48, attention_head_dim=64, in_channels=96, out_channels=56, flip_sin_to_cos=True,
@@ -134,6 +134,9 @@ class AetherTransformer3D(nn.Module):
         # isolated but has not been A/B-timed in the power-capped step).  AETHER_ATTENTION_MODE overrides it.
         import os
         self.attention_fp16_pv = int(os.environ.get("AETHER_ATTENTION_MODE", "5"))
+        # QK-LayerNorm + RoPE inside the QKV GEMM epilogue (one launch less per layer; measured slower: off).  Read here,
+        # once per module, and stored in the handle's config -- the C library itself never reads the environment.
+        self.fused_qkv_epilogue = os.environ.get("AETHER_FUSED_QK", "0")[:1] == "1"
 
     # ------------------------------------------------------------------ torch plumbing
     @property
@@ -213,6 +216,7 @@ class AetherTransformer3D(nn.Module):
 
     # ------------------------------------------------------------------ packing + native handle
     @torch.no_grad()
+    @device_guard
     def pack(self, release_unpacked: bool = False):
         """Lay the weights out for the kernels and create the native handle (idempotent)."""
         lib = _lib.require_device()
@@ -285,7 +289,8 @@ class AetherTransformer3D(nn.Module):
         w.layers = C.cast(layers, C.POINTER(DitLayerWeights))
         cfg = DitConfig(c.num_attention_heads, c.attention_head_dim, c.num_layers, c.in_channels, c.out_channels,
                         c.patch_size, c.time_embed_dim, c.text_embed_dim, int(c.flip_sin_to_cos), float(c.freq_shift),
-                        float(c.norm_eps), c.ff_mult, int(self.attention_fp16_pv))
+                        float(c.norm_eps), c.ff_mult, int(self.attention_fp16_pv),
+                        int(self.fused_qkv_epilogue and c.attention_head_dim == 64))
         h = C.c_void_p()
         check(lib.aether_dit_create(C.byref(cfg), C.byref(w), C.byref(h)), "dit_create")
         self._handle = h
@@ -295,19 +300,22 @@ class AetherTransformer3D(nn.Module):
         return self
 
     def _pos_embedding_for(self, St, F, H, W):
-        """diffusers CogVideoXPatchEmbed: learned table when the geometry equals the sample geometry, else a
-        freshly computed 3-D sin-cos table (zeros on the text rows).  Returns bf16 [St+Sv, D] or None."""
+        """diffusers CogVideoXPatchEmbed adds a positional table when `use_learned_positional_embeddings` OR
+        `not use_rotary_positional_embeddings` (the 2B-style fixed sin-cos branch): the stored table when the geometry
+        equals the sample geometry and the table is learned, else a freshly computed 3-D sin-cos table (zeros on the
+        text rows).  Returns bf16 [St+Sv, D], or None for the rotary-only configuration (AetherV1)."""
         c = self.config
-        if not c.use_learned_positional_embeddings:
+        learned = bool(c.use_learned_positional_embeddings)
+        if not learned and c.use_rotary_positional_embeddings:
             return None
         key = (St, F, H, W)
         cache = self._packed.setdefault("pos_cache", {})
         if key in cache:
             return cache[key]
-        if H != c.sample_height or W != c.sample_width:
+        if learned and (H != c.sample_height or W != c.sample_width):
             raise ValueError("learned positional embeddings require the sample height/width (diffusers behaviour)")
         pre = (F - 1) * c.temporal_compression_ratio + 1
-        if pre == c.sample_frames:
+        if learned and pre == c.sample_frames:
             pos = self.patch_embed.pos_embedding[0, :St + F * (H // 2) * (W // 2)]
         else:
             from .posembed import sincos_3d_joint
@@ -332,12 +340,12 @@ class AetherTransformer3D(nn.Module):
         """Kernels of this library launched by one forward (see csrc/dit_forward.cu): 8 per layer (LN-modulate, QKV,
         QK-norm+RoPE, attention, to_out, LN-modulate, FF1, FF2); 7 with AETHER_FUSED_QK=1 (QK-norm+RoPE in the QKV
         epilogue)."""
-        import os
-        per_layer = 7 if os.environ.get("AETHER_FUSED_QK", "0")[:1] == "1" and self.config.attention_head_dim == 64 else 8
+        per_layer = 7 if self.fused_qkv_epilogue and self.config.attention_head_dim == 64 else 8
         return 4 + 1 + 2 * batch + per_layer * self.config.num_layers + 1 + batch + 1
 
     # ------------------------------------------------------------------ loop form: concat / repeat / expand folded in
     @torch.no_grad()
+    @device_guard
     def forward_split(self, latents: torch.Tensor, condition: torch.Tensor, encoder_hidden_states: torch.Tensor,
                       timestep: torch.Tensor, image_rotary_emb=None):
         """Reference :832-875 in one C-ABI call: `latents` [1 or B, F, C0, H, W] is broadcast over the batch of
@@ -373,6 +381,7 @@ class AetherTransformer3D(nn.Module):
 
     # ------------------------------------------------------------------ forward = one C-ABI call
     @torch.no_grad()
+    @device_guard
     def forward(self, hidden_states: torch.Tensor, encoder_hidden_states: torch.Tensor, timestep: torch.Tensor,
                 timestep_cond=None, ofs=None, image_rotary_emb: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
                 attention_kwargs=None, return_dict: bool = False):

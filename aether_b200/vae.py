@@ -25,7 +25,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib, ops
-from ._lib import check, current_stream, ptr
+from ._lib import check, current_stream, ptr, device_guard
 
 BF16 = torch.bfloat16
 
@@ -101,6 +101,11 @@ class _Posterior:
         self.m = moments_cl
         self.L = latent_channels
 
+    @property
+    def device(self):
+        return self.m.device
+
+    @device_guard
     def _run(self, noise):
         T, h, w, Cp = self.m.shape
         z = torch.empty(1, self.L, T, h, w, dtype=BF16, device=self.m.device)
@@ -226,6 +231,7 @@ class AetherVAE(nn.Module):
 
     # ------------------------------------------------------------------ packing
     @torch.no_grad()
+    @device_guard
     def pack(self):
         if self._packed is not None:
             return self
@@ -518,6 +524,7 @@ class AetherVAE(nn.Module):
 
     # ------------------------------------------------------------------ public API
     @torch.no_grad()
+    @device_guard
     def encode(self, x: torch.Tensor, return_dict: bool = True):
         _lib.require_device()
         self.pack()
@@ -529,6 +536,7 @@ class AetherVAE(nn.Module):
         return SimpleNamespace(latent_dist=post)
 
     @torch.no_grad()
+    @device_guard
     def decode(self, z: torch.Tensor, return_dict: bool = True):
         _lib.require_device()
         self.pack()

@@ -35,7 +35,7 @@ extern "C" {
 #define AETHER_ERR_CUDA 2      /* CUDA runtime / driver error (message on stderr) */
 #define AETHER_ERR_WORKSPACE 3 /* workspace too small */
 
-#define AETHER_ABI_VERSION 1
+#define AETHER_ABI_VERSION 2
 int32_t aether_abi_version(void);
 /* 1 when a CUDA device of compute capability 10.x is present, else 0 (never throws). */
 int32_t aether_device_ok(void);
@@ -49,7 +49,7 @@ int32_t aether_device_ok(void);
  * Output columns >= f16_from_col (a multiple of 8; < 0 = none) are written as fp16 instead of bf16 (used for
  * the V third of the fused QKV projection when the fp16-PV attention mode is on).
  * M >= 1024 runs on CTA pairs (tcgen05 cta_group::2, cluster of two CTAs per 256 x 256 tile), smaller M on single
- * CTAs; results are identical.  Environment variable AETHER_GEMM_1CTA=1 forces the single-CTA kernel (A/B timing).
+ * CTAs; results are identical.
  * Replaces nn.Linear inside CogVideoXBlock / CogVideoXPatchEmbed / proj_out (pipeline :865). */
 int aether_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int32_t M,
                      int32_t N, int32_t K, const float* bias, int32_t epilogue, const float* gate_vid,
@@ -124,6 +124,8 @@ typedef struct AetherDitConfig {
   int32_t ff_mult;
   int32_t attention_fp16_pv;   /* attention variant id passed to aether_attention_bf16 (5 = product default); for
                                   ids 1 and 2 the QKV GEMM emits the V third as fp16 */
+  int32_t fused_qkv_epilogue;  /* 1: QK-LayerNorm + RoPE run inside the QKV GEMM epilogue (one launch less per layer;
+                                  measured slower, default 0).  Per handle -- the library reads no environment. */
 } AetherDitConfig;
 
 typedef struct AetherDitLayerWeights {

@@ -78,12 +78,18 @@ def tiny_config(**kw) -> DiTConfig:
 
 def timestep_sinusoid(timesteps: torch.Tensor, dim: int, flip_sin_to_cos: bool, shift: float,
                       max_period: float = 10000.0) -> torch.Tensor:
-    """diffusers get_timestep_embedding (scale=1)."""
+    """diffusers get_timestep_embedding (scale=1): fp32 `exponent`, fp32 angle `t * exp(exponent)`, fp32 sin/cos.
+
+    The three transcendentals are evaluated in float64 on the fp32 operand and rounded back to fp32, i.e. the
+    correctly rounded fp32 result.  torch's own fp32 exp/sin/cos go through a per-ISA vector math library whose last
+    bit differs between hosts, and a 1-ulp change of a frequency moves the angle of t = 999 by 6e-5 -- enough to make
+    goldens generated from this oracle host-dependent (observed: MKL AVX2 vs AVX-512 paths)."""
     half = dim // 2
     exponent = -math.log(max_period) * torch.arange(half, dtype=torch.float32)
     exponent = exponent / (half - shift)
-    emb = timesteps[:, None].float() * torch.exp(exponent)[None, :]
-    emb = torch.cat([torch.sin(emb), torch.cos(emb)], dim=-1)
+    freq = torch.exp(exponent.double()).float()
+    emb = timesteps[:, None].float() * freq[None, :]
+    emb = torch.cat([torch.sin(emb.double()), torch.cos(emb.double())], dim=-1).float()
     if flip_sin_to_cos:
         emb = torch.cat([emb[:, half:], emb[:, :half]], dim=-1)
     return emb

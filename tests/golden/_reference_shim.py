@@ -45,7 +45,7 @@ def install():
     from transformers import AutoTokenizer, T5EncoderModel  # noqa: F401   `accelerate` with importlib at import)
     from oracle.rope import get_1d_rotary_pos_embed as _oracle_rope1d
     from oracle.scheduler import OracleDPMScheduler
-    from aether_b200.pipeline import VideoProcessor
+    from oracle.video_processor import OracleVideoProcessor as VideoProcessor   # independent of the product's copy
 
     # ---------------------------------------------------------------- diffusers
     d = _mod("diffusers")

@@ -9,8 +9,10 @@ What is pinned (files under /root/reference executed unmodified through tests/go
                     (tile plan, compute_scale, spatial + temporal blend chain) with a deterministic stand-in
                     for the per-tile pipeline call (tests/helpers.py::fake_tile_outputs)
   pipeline_*.npz    aether/pipelines/aetherv1_pipeline_cogvideox.py:350-965           check/preprocess/prepare_latents/
-                    __call__ (reconstruction, prediction with raymap + dynamic CFG, planning) driving the bf16
-                    oracle modules (tests/helpers.py::tiny_oracle_modules) on CPU with a CPU generator.
+                    __call__ (reconstruction, prediction with raymap + dynamic CFG, planning) driving the oracle
+                    modules with float64 arithmetic and bf16 module I/O (tests/helpers.py::exact_oracle_modules) on
+                    CPU with a CPU generator -- portable across hosts (round 1 used bf16 CPU modules whose rounding
+                    followed the host ISA); diffusers' VideoProcessor stand-in = oracle/video_processor.py.
 The third-party diffusers modules themselves stay "parity unpinned" (see oracle/__init__.py).
 """
 from __future__ import annotations
@@ -28,7 +30,7 @@ sys.path.insert(0, str(HERE.parent.parent))
 
 import _reference_shim as shim  # noqa: E402
 from helpers import (TINY, empty_prompt_embeds, fake_tile_outputs, subsample, synthetic_long_clip,  # noqa: E402
-                     synthetic_raymap, synthetic_video, tiny_oracle_modules)
+                     synthetic_raymap, synthetic_video, exact_oracle_modules)
 
 
 def make_rope():
@@ -138,7 +140,7 @@ def make_sliding():
 
 def make_pipeline():
     P = shim.reference_pipeline_module()
-    dit, vae, sched = tiny_oracle_modules(torch.bfloat16)
+    dit, vae, sched = exact_oracle_modules()
     emb = empty_prompt_embeds()
     pipe = P.AetherV1PipelineCogVideoX(tokenizer=None, text_encoder=lambda prompt: emb, vae=vae, scheduler=sched,
                                        transformer=dit)

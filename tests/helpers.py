@@ -24,6 +24,58 @@ def tiny_oracle_modules(dtype=torch.bfloat16, seed=0):
     return dit.to(dtype), vae.to(dtype), OracleDPMScheduler()
 
 
+class _ExactDiT:
+    """fp64-compute / bf16-I/O adapter around the oracle DiT: the module boundary the reference pipeline sees is
+    the production one (bf16 tensors in, bf16 out, :865-875) while the arithmetic in between is float64, so the
+    result does not depend on the host's bf16/fp32 GEMM kernels (oneDNN picks them per ISA).  Golden fixtures made
+    with these modules are portable across x86 hosts up to rare single-ulp bf16 rounding flips."""
+
+    def __init__(self, dit):
+        self.inner = dit.double()
+        self.config = dit.config
+        self.dtype = torch.bfloat16
+
+    def __call__(self, hidden_states, encoder_hidden_states, timestep, ofs=None, image_rotary_emb=None,
+                 attention_kwargs=None, return_dict=False):
+        rot = None if image_rotary_emb is None else tuple(r.double() for r in image_rotary_emb)
+        out = self.inner(hidden_states.double(), encoder_hidden_states.double(), timestep, ofs=ofs,
+                         image_rotary_emb=rot)[0]
+        return (out.to(hidden_states.dtype),)
+
+
+class _ExactVAE:
+    """Same adapter for the VAE: encode/decode compute in float64, posterior parameters / decoded sample are handed
+    back in the caller's dtype (so the posterior noise is drawn in bf16 exactly like the production path)."""
+
+    def __init__(self, vae):
+        self.inner = vae.double()
+        self.config = vae.config
+        self.dtype = torch.bfloat16
+
+    def enable_slicing(self):
+        self.inner.enable_slicing()
+
+    def enable_tiling(self):
+        self.inner.enable_tiling()
+
+    def encode(self, x):
+        from types import SimpleNamespace
+        from oracle.vae import DiagonalGaussian
+        h = self.inner.encode(x.double()).latent_dist.parameters
+        return SimpleNamespace(latent_dist=DiagonalGaussian(h.to(x.dtype)))
+
+    def decode(self, z):
+        from types import SimpleNamespace
+        return SimpleNamespace(sample=self.inner.decode(z.double()).sample.to(z.dtype))
+
+
+def exact_oracle_modules(seed=0):
+    """(transformer, vae, scheduler) for the tiny geometry: same seeded bf16-representable weights as
+    `tiny_oracle_modules`, float64 arithmetic, bf16 module I/O.  Used for the PORTABLE pipeline goldens."""
+    dit, vae, sched = tiny_oracle_modules(torch.float32, seed)
+    return _ExactDiT(dit), _ExactVAE(vae), sched
+
+
 def empty_prompt_embeds(seed=7):
     g = torch.Generator().manual_seed(seed)
     return (torch.randn(1, TINY["text_len"], TINY["text_dim"], generator=g) * 0.2).bfloat16()

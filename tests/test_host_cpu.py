@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in include/aether_b200.h but not exported"
     assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
     loaded = _lib.load()
-    assert loaded.aether_abi_version() == 1
+    assert loaded.aether_abi_version() == 2
 
 
 def test_ctypes_signatures_match_header_prototypes():

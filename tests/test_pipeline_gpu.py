@@ -1,11 +1,12 @@
 """End-to-end on the GPU: aether_b200.pipeline with the three CUDA modules (AetherTransformer3D, AetherVAE,
 AetherDPMScheduler) against the golden outputs of the REFERENCE pipeline (tests/golden/pipeline_*.npz, produced by
-the reference's own __call__ driving the bf16 torch oracle modules on CPU with the same seed).
+the reference's own __call__ driving the oracle modules -- float64 arithmetic, bf16 module I/O -- on CPU with the
+same seed; the fixture is host-independent, see tests/test_oracle_golden.py).
 
 Identical weights (bf16-rounded), identical inputs, identical CPU generator => identical noise stream; what
-differs is bf16 arithmetic order inside the kernels, propagated through 2-3 DPM steps and the VAE decode.
-Stated tolerance: rel-RMS <= 6e-2 on the denoised latents, the disparity and the raymap; rgb (clamped to [0, 1])
-mean-abs error <= 0.02 / max-abs <= 0.3.  (Measured on a B200: latents 0.8-1.2 %, rgb mean 0.5 %.)
+differs is the bf16 storage of intermediates inside the kernels (fp32 accumulation), propagated through 2-3 DPM
+steps and the VAE decode.  Stated tolerance: rel-RMS <= 2e-2 on the denoised latents, the disparity and the
+raymap; rgb (clamped to [0, 1]) mean-abs error <= 0.01 / max-abs <= 0.2.
 Also: the sliding-window blend on the device (K10) against the reference's blend golden: fp64 buffers, tolerance
 rel 2e-6 -- the only difference is the summation order of the fp32 products inside compute_scale (the reference
 reduces in fp32 with torch.sum, the kernel accumulates the same fp32 products in fp64), i.e. ~1e-7 on the scale.
@@ -72,11 +73,11 @@ def test_pipeline_matches_reference_golden(golden_dir, name, kw):
     print(f"{name}: latents rel-rms {rel_lat:.4f}; disparity mean/max err {d_err.mean():.4f}/{d_err.max():.4f}; "
           f"rgb mean/max err {r_err.mean():.4f}/{r_err.max():.4f}; raymap rel-rms {rel_ray:.4f}")
     rel_disp = _rel(out.disparity, g["disparity"])
-    assert rel_lat <= 6e-2
+    assert rel_lat <= 2e-2
     # disparity = (mean_c(decode) * 0.5 + 0.5)^2 is unbounded with the synthetic VAE weights -> relative metric
-    assert rel_disp <= 6e-2, rel_disp
-    assert r_err.mean() <= 0.02 and r_err.max() <= 0.3
-    assert rel_ray <= 6e-2
+    assert rel_disp <= 2e-2, rel_disp
+    assert r_err.mean() <= 0.01 and r_err.max() <= 0.2
+    assert rel_ray <= 2e-2
 
 
 @pytest.mark.parametrize("name", ["temporal", "horizontal", "vertical", "long"])
