@@ -97,13 +97,16 @@ SIGNATURES = {
                                     c_int32, c_void_p]),
     "aether_cfg_dpm_step": (C.c_int, [c_void_p, c_int32, c_int32, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
                                       C.POINTER(DpmCoeffs), c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "aether_scale_reduce_work_bytes": (c_int64, []),
     "aether_scale_reduce": (C.c_int, [c_void_p, c_int32, c_int64, c_int64, c_void_p, c_int32, c_int64, c_int64,
                                       c_int64, c_int64, c_int64, c_void_p, c_void_p]),
     "aether_blend_crossfade": (C.c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int32, c_int64, c_int64, c_void_p,
-                                         c_int32, c_int64, c_int64, c_double, c_int64, c_int64, c_int64, c_int32,
-                                         c_void_p]),
+                                         c_int32, c_int64, c_int64, c_double, c_void_p, c_int64, c_int64, c_int64,
+                                         c_int32, c_void_p]),
     "aether_scale_copy": (C.c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int32, c_int64, c_int64, c_double,
-                                    c_int32, c_int64, c_int64, c_int64, c_void_p]),
+                                    c_void_p, c_int32, c_int64, c_int64, c_int64, c_void_p]),
+    "aether_disparity_to_depth": (C.c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int32, c_int64, c_int64, c_int64,
+                                            c_int64, c_int64, c_void_p]),
 }
 
 
@@ -129,7 +132,11 @@ def load():
     return lib
 
 
+CALLS = [0]     # C-ABI calls that went through check() (bench.py derives its kernel-launch count from it)
+
+
 def check(status: int, what: str):
+    CALLS[0] += 1
     if status != 0:
         raise RuntimeError(f"aether_b200: {what} failed with status {status} ({STATUS.get(status, '?')})")
 

@@ -107,7 +107,7 @@ class VideoProcessor:
             arr = image if image.ndim == 4 else image[None]
         if arr.ndim == 3:
             arr = arr[..., None]
-        if device is not None and torch.device(device).type == "cuda" and arr.dtype == np.float32:
+        if device is not None and torch.device(device).type == "cuda" and arr.dtype in (np.float32, np.float64):
             t = torch.from_numpy(np.ascontiguousarray(arr)).to(device).permute(0, 3, 1, 2).contiguous()
         else:
             t = torch.from_numpy(np.ascontiguousarray(arr.transpose(0, 3, 1, 2)))
@@ -120,14 +120,16 @@ class VideoProcessor:
 
     @staticmethod
     def postprocess_video(video: torch.Tensor, output_type: str = "np"):
-        """video [B, C, F, H, W] in [-1, 1] -> np.float32 [B, F, H, W, C] in [0, 1]."""
+        """video [B, C, F, H, W] in [-1, 1] -> float32 [B, F, H, W, C] in [0, 1]: numpy ("np", like the reference :932)
+        or a tensor on the video's device ("pt")."""
         outs = []
         for b in range(video.shape[0]):
             v = video[b].permute(1, 0, 2, 3)
             v = (v / 2 + 0.5).clamp(0, 1)
             # layout change and widening on the tensor's own device (exact), then one contiguous copy to the host
-            outs.append(v.permute(0, 2, 3, 1).float().contiguous().cpu().numpy())
-        return np.stack(outs)
+            v = v.permute(0, 2, 3, 1).float().contiguous()
+            outs.append(v if output_type == "pt" else v.cpu().numpy())
+        return torch.stack(outs) if output_type == "pt" else np.stack(outs)
 
 
 @dataclass
@@ -309,6 +311,13 @@ class AetherV1PipelineCogVideoX:
 
     # ------------------------------------------------------------------ reference :451-512
     def _preprocess_image(self, image, height, width, device=None):
+        if (isinstance(image, torch.Tensor) and image.is_cuda and image.is_floating_point() and image.ndim == 4
+                and tuple(image.shape[1:]) == (height, width, 3) and height % self.vae_scale_factor_spatial == 0
+                and width % self.vae_scale_factor_spatial == 0):
+            # frames already resident on the device at the target size [F, H, W, 3]: the centre crop (:451-458) and
+            # the resize are identities, what remains is the layout change and 2x - 1 in the frames' own dtype --
+            # the same IEEE operations the host path performs, without the reference's .cpu().numpy() round trip
+            return 2.0 * image.permute(0, 3, 1, 2) - 1.0
         if isinstance(image, torch.Tensor):
             image = image.cpu().numpy()
         if image.dtype == np.uint8:
@@ -412,7 +421,14 @@ class AetherV1PipelineCogVideoX:
                  num_inference_steps: Optional[int] = None, timesteps: Optional[List[int]] = None,
                  guidance_scale: Optional[float] = None, use_dynamic_cfg: bool = False,
                  num_videos_per_prompt: int = 1, eta: float = 0.0, generator=None, return_dict: bool = True,
-                 attention_kwargs: Optional[Dict] = None, fps: Optional[int] = None, output_latents: bool = False):
+                 attention_kwargs: Optional[Dict] = None, fps: Optional[int] = None, output_latents: bool = False,
+                 output_type: str = "np", decode_rgb: bool = True):
+        """Reference signature (:691-712) plus three extensions that default to the reference behaviour:
+        `output_latents` (return the denoised latents, tests), `output_type="pt"` (rgb / disparity / raymap stay
+        float32 CUDA tensors -- the sliding-window path keeps per-tile disparities on the device), `decode_rgb=False`
+        (skip the rgb VAE decode; rgb is then None -- the sliding-window evaluation only uses the rgb of tile 0)."""
+        if output_type not in ("np", "pt"):
+            raise ValueError("`output_type` has to be 'np' or 'pt'.")
         if task is None:
             task = "reconstruction" if video is not None else ("planning" if goal is not None else "prediction")
         tc = self.transformer.config
@@ -537,19 +553,27 @@ class AetherV1PipelineCogVideoX:
         disparity_latents = latents[:, :, lc:lc * 2]
         camera_latents = latents[:, :, lc * 2:]
 
-        rgb_video = self.decode_latents(rgb_latents)
-        rgb_video = self.video_processor.postprocess_video(video=rgb_video, output_type="np")
+        to_host = output_type == "np"
+        rgb_video = None
+        if decode_rgb:
+            rgb_video = self.decode_latents(rgb_latents)
+            rgb_video = self.video_processor.postprocess_video(video=rgb_video, output_type=output_type)
         disparity_video = self.decode_latents(disparity_latents)
+        n_out_frames = disparity_video.shape[2]
         disparity_video = disparity_video.mean(dim=1, keepdim=False)
         disparity_video = disparity_video * 0.5 + 0.5
         disparity_video = torch.square(disparity_video)
-        disparity_video = disparity_video.float().cpu().numpy()
+        disparity_video = disparity_video.float()
+        if to_host:
+            disparity_video = disparity_video.cpu().numpy()
         # einops "b t (n c) h w -> b (n t) c h w", n = 4, keep the last F frames   (:942-949)
         b, tl, nc, h, w = camera_latents.shape
         rm = camera_latents.reshape(b, tl, 4, nc // 4, h, w).permute(0, 2, 1, 3, 4, 5).reshape(b, 4 * tl, nc // 4, h, w)
-        raymap_out = rm[:, -rgb_video.shape[1]:, :, :].float().cpu().numpy()
+        raymap_out = rm[:, -n_out_frames:, :, :].float()
+        if to_host:
+            raymap_out = raymap_out.cpu().numpy()
         self.maybe_free_model_hooks()
         if not return_dict:
             return (rgb_video, disparity_video, raymap_out)
-        return AetherV1PipelineOutput(rgb=rgb_video.squeeze(0), disparity=disparity_video.squeeze(0),
-                                      raymap=raymap_out.squeeze(0))
+        sq = lambda a: None if a is None else a.squeeze(0)
+        return AetherV1PipelineOutput(rgb=sq(rgb_video), disparity=sq(disparity_video), raymap=sq(raymap_out))

@@ -7,14 +7,19 @@ per tile with a freshly seeded generator (:151-158), spatial then temporal blend
 
 What changes, B200-first:
   * the reference runs the tiles serially in one process (it can only shard whole sequences, :320-323);
-    here the flattened tile list (reference order k = t_idx * n_spatial + i) is partitioned round-robin
-    over the ranks of a torch.distributed group, every rank runs its tiles on its own GPU, and ONE
-    all-gather (NCCL over NVLink/NVSwitch) of the fp32 disparity tiles precedes the blend;
-  * the blend chain itself (sequential and order-sensitive, :166-285) is executed on the device with the K10
-    kernels, in the reference's order, into one fp64 buffer in place (the reference re-allocates an
-    np.ones(float64) result per step; element-wise the arithmetic is identical).
-Return value = the reference's: (final_rgb fp32 [F,480,720,3] = first tile of the first window (:173-176,
-:265-266), final_disparity fp64 [T,H,W]).
+    here the flattened tile list (reference order k = t_idx * n_spatial + i) is dealt round-robin over the
+    ranks of a torch.distributed group and processed in ROUNDS: in round j rank r runs tile j * N + r on its
+    own GPU (weights replicated), the per-tile disparity stays on the device (pipeline output_type="pt");
+  * exchange: after each round the N - 1 fp32 disparity tiles of the round travel once, peer to peer, to the
+    blend rank (NCCL send/recv over NVLink / NVSwitch, 56.7 MB per tile) -- nothing is replicated to everyone;
+  * the blend chain itself (sequential and order-sensitive, :166-285) STREAMS behind the tile compute on the
+    blend rank: a window is spatially blended and appended to the temporal chain as soon as its tiles have
+    arrived, in the reference's order, into one fp64 buffer in place (the reference re-allocates an
+    np.ones(float64) result per step; element-wise the arithmetic is identical) with the K10 kernels; the
+    masked-LSQ scale of every window stays in device memory (no host synchronisation in the chain).
+Return value on the blend rank = the reference's: (final_rgb fp32 [F,480,720,3] = first tile of the first
+window (:173-176, :265-266), final_disparity fp64 [T,H,W]); other ranks get (None, None) unless
+`result_on_all_ranks` asks for a broadcast.
 """
 from __future__ import annotations
 
@@ -26,7 +31,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import check, current_stream
+from ._lib import check, current_stream, device_guard
 
 
 # ------------------------------------------------------------------------------------------ tiling plan
@@ -93,31 +98,15 @@ def plan_windows(t: int, h: int, w: int, total_frames: Optional[int] = None) -> 
     return Plan(tuple(tiles), len(t_starts), num_windows, is_horizontal, max_frames_per_window)
 
 
+def tile_owner(k: int, world_size: int) -> int:
+    """Round-robin deal: tile k is run by rank k % N in round k // N (consecutive tiles -- the spatial tiles of one
+    temporal window -- land on different GPUs, and the windows complete in chain order)."""
+    return k % world_size
+
+
 def partition_tiles(n_tiles: int, rank: int, world_size: int) -> List[int]:
-    """Round-robin: consecutive tiles (which share a temporal window) land on different GPUs."""
+    """Tiles run by `rank`, in round order."""
     return list(range(rank, n_tiles, world_size))
-
-
-# ------------------------------------------------------------------------------------------ exchange step
-def gather_tiles(local: Sequence[Tuple[int, torch.Tensor]], n_tiles: int, rank: int, world_size: int,
-                 group=None) -> List[torch.Tensor]:
-    """All-gather the per-tile disparity tensors (all of identical shape) so that every rank holds the full,
-    reference-ordered list.  One collective; with NCCL it runs over NVLink/NVSwitch."""
-    if world_size == 1:
-        out = [None] * n_tiles
-        for k, d in local:
-            out[k] = d
-        return out
-    import torch.distributed as dist
-    n_max = (n_tiles + world_size - 1) // world_size
-    ref = local[0][1]
-    send = torch.zeros((n_max,) + tuple(ref.shape), dtype=ref.dtype, device=ref.device)
-    for j, (k, d) in enumerate(local):
-        assert k == rank + j * world_size
-        send[j].copy_(d)
-    recv = torch.empty((world_size * n_max,) + tuple(ref.shape), dtype=ref.dtype, device=ref.device)
-    dist.all_gather_into_tensor(recv, send, group=group)      # rank r's block lands at rows [r*n_max, (r+1)*n_max)
-    return [recv[(k % world_size) * n_max + k // world_size] for k in range(n_tiles)]
 
 
 # ------------------------------------------------------------------------------------------ K10 wrappers
@@ -126,32 +115,51 @@ def _v3(t: torch.Tensor):
     return t.data_ptr(), int(t.dtype == torch.float64), t.stride(0), t.stride(1)
 
 
-def compute_scale(prediction: torch.Tensor, target: torch.Tensor) -> float:
-    """compute_scale(prediction, target, ones) of postprocess_utils.py:847-864 on CUDA views [n0,n1,n2]."""
+def _new_work(device) -> torch.Tensor:
+    """Device scratch of aether_scale_reduce: {sum(p*t), sum(p*p)} as fp64 + block counter + per-block partials."""
+    n = _lib.require_device().aether_scale_reduce_work_bytes()
+    return torch.zeros((n + 7) // 8, dtype=torch.float64, device=device)
+
+
+@device_guard
+def scale_sums_(work: torch.Tensor, prediction: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """Enqueue compute_scale's two sums (postprocess_utils.py:847-864, mask of ones) over CUDA views [n0,n1,n2];
+    the result stays in `work[:2]` on the device (no synchronisation)."""
     lib = _lib.require_device()
-    out = torch.zeros(2, dtype=torch.float64, device=prediction.device)
     pp, pf, p0, p1 = _v3(prediction)
     tp, tf, t0, t1 = _v3(target)
     n0, n1, n2 = prediction.shape
     assert tuple(target.shape) == (n0, n1, n2)
-    check(lib.aether_scale_reduce(pp, pf, p0, p1, tp, tf, t0, t1, n0, n1, n2, out.data_ptr(), current_stream()),
+    check(lib.aether_scale_reduce(pp, pf, p0, p1, tp, tf, t0, t1, n0, n1, n2, work.data_ptr(), current_stream()),
           "scale_reduce")
-    num, den = out.tolist()
+    return work
+
+
+def compute_scale(prediction: torch.Tensor, target: torch.Tensor) -> float:
+    """compute_scale(prediction, target, ones) as a python float (synchronises; the blend chain itself never calls
+    this -- it consumes the device-resident sums)."""
+    work = scale_sums_(_new_work(prediction.device), prediction, target)
+    num, den = work[:2].tolist()
     num32, den32 = np.float32(num), np.float32(den)     # the reference holds both sums in fp32
     return float(num32 / den32) if den32 != 0 else 0.0
 
 
-def _crossfade_(dst: torch.Tensor, acc: torch.Tensor, win: torch.Tensor, scale: float, axis: int):
+@device_guard
+def _crossfade_(dst: torch.Tensor, acc: torch.Tensor, win: torch.Tensor, axis: int, scale: float = 1.0,
+                sums: Optional[torch.Tensor] = None):
     lib = _lib.require_device()
     assert dst.dtype == torch.float64 and dst.shape == acc.shape == win.shape
     ap, af, a0, a1 = _v3(acc)
     wp, wf, w0, w1 = _v3(win)
     n0, n1, n2 = dst.shape
     check(lib.aether_blend_crossfade(dst.data_ptr(), dst.stride(0), dst.stride(1), ap, af, a0, a1, wp, wf, w0, w1,
-                                     float(scale), n0, n1, n2, axis, current_stream()), "blend_crossfade")
+                                     float(scale), 0 if sums is None else sums.data_ptr(), n0, n1, n2, axis,
+                                     current_stream()), "blend_crossfade")
 
 
-def _scale_copy_(dst: torch.Tensor, src: torch.Tensor, scale: float, apply_scale: bool):
+@device_guard
+def _scale_copy_(dst: torch.Tensor, src: torch.Tensor, apply_scale: bool, scale: float = 1.0,
+                 sums: Optional[torch.Tensor] = None):
     lib = _lib.require_device()
     assert dst.dtype == torch.float64 and dst.shape == src.shape
     if dst.numel() == 0:
@@ -159,84 +167,302 @@ def _scale_copy_(dst: torch.Tensor, src: torch.Tensor, scale: float, apply_scale
     sp, sf, s0, s1 = _v3(src)
     n0, n1, n2 = dst.shape
     check(lib.aether_scale_copy(dst.data_ptr(), dst.stride(0), dst.stride(1), sp, sf, s0, s1, float(scale),
-                                int(apply_scale), n0, n1, n2, current_stream()), "scale_copy")
+                                0 if sums is None else sums.data_ptr(), int(apply_scale), n0, n1, n2,
+                                current_stream()), "scale_copy")
 
 
-def blend_chain(windows: Sequence[torch.Tensor], ranges: Sequence[Tuple[int, int]], axis: int) -> torch.Tensor:
+@device_guard
+def disparity_to_depth_device(disparity: torch.Tensor) -> torch.Tensor:
+    """launch_aether.py:347 on the device: fp64 depth = clip(1 / disparity, 0, 100) of a CUDA [T,H,W] tensor."""
+    lib = _lib.require_device()
+    out = torch.empty(disparity.shape, dtype=torch.float64, device=disparity.device)
+    sp, sf, s0, s1 = _v3(disparity)
+    n0, n1, n2 = disparity.shape
+    check(lib.aether_disparity_to_depth(out.data_ptr(), out.stride(0), out.stride(1), sp, sf, s0, s1, n0, n1, n2,
+                                        current_stream()), "disparity_to_depth")
+    return out
+
+
+def _axis_slices(axis: int):
+    return lambda a, b: tuple(slice(a, b) if d == axis else slice(None) for d in range(3))
+
+
+def _append_(buf: torch.Tensor, win: torch.Tensor, start: int, prev_end: int, axis: int, work: torch.Tensor):
+    """One link of the reference's chain (:193-250 spatial / :268-284 temporal), in place on `buf`: `win` covers
+    [start, start + n) on `axis`, the accumulation so far ends at `prev_end`."""
+    sl = _axis_slices(axis)
+    overlap = prev_end - start
+    n_win = win.shape[axis]
+    scale_sums_(work, win[sl(0, overlap)], buf[sl(start, prev_end)])
+    _crossfade_(buf[sl(start, prev_end)], buf[sl(start, prev_end)], win[sl(0, overlap)], axis, sums=work)
+    _scale_copy_(buf[sl(prev_end, start + n_win)], win[sl(overlap, n_win)], True, sums=work)
+
+
+def blend_chain(windows: Sequence[torch.Tensor], ranges: Sequence[Tuple[int, int]], axis: int,
+                out: Optional[torch.Tensor] = None, work: Optional[torch.Tensor] = None) -> torch.Tensor:
     """The reference's sequential blend along `axis` (2 = width / 1 = height: launch_aether.py:166-252;
     0 = time: :259-285).  windows[i] covers [ranges[i][0], ranges[i][1]) on that axis.  Returns windows[0]
-    itself when there is a single window (dtype preserved like the reference), else an fp64 tensor."""
+    itself when there is a single window (dtype preserved like the reference), else an fp64 tensor (`out` when
+    given).  Nothing here synchronises with the host."""
     if len(windows) == 1:
         return windows[0]
     w0 = windows[0]
     full = list(w0.shape)
     full[axis] = max(r[1] for r in ranges)
-    buf = torch.empty(full, dtype=torch.float64, device=w0.device)
-    sl = lambda a, b: tuple(slice(a, b) if d == axis else slice(None) for d in range(3))
-    _scale_copy_(buf[sl(ranges[0][0], ranges[0][1])], w0, 1.0, False)
+    buf = out if out is not None else torch.empty(full, dtype=torch.float64, device=w0.device)
+    assert list(buf.shape) == full and buf.dtype == torch.float64
+    work = work if work is not None else _new_work(w0.device)
+    sl = _axis_slices(axis)
+    _scale_copy_(buf[sl(ranges[0][0], ranges[0][1])], w0, False)
     for idx in range(1, len(windows)):
-        win = windows[idx]
-        start = ranges[idx][0]
-        prev_end = ranges[idx - 1][1]
-        overlap = prev_end - start
-        n_win = win.shape[axis]
-        scale = compute_scale(win[sl(0, overlap)], buf[sl(start, prev_end)])
-        _crossfade_(buf[sl(start, prev_end)], buf[sl(start, prev_end)], win[sl(0, overlap)], scale, axis)
-        _scale_copy_(buf[sl(prev_end, start + n_win)], win[sl(overlap, n_win)], scale, True)
+        _append_(buf, windows[idx], ranges[idx][0], ranges[idx - 1][1], axis, work)
     return buf
 
 
+class StreamingBlend:
+    """The blend rank's state: windows are pushed in temporal order as their tiles arrive; each push enqueues the
+    spatial blend of the window (reference :166-252) and one link of the temporal chain (:259-285) on the current
+    stream.  `final` is the reference's final_disparity (fp64 [T, H, W]) once every window has been pushed."""
+
+    def __init__(self, plan: Plan, t: int, h: int, w: int, device):
+        self.plan = plan
+        self.device = torch.device(device)
+        self.final = torch.empty((t, h, w), dtype=torch.float64, device=self.device) if plan.n_temporal > 1 else None
+        self._win = (torch.empty((plan.frames_per_window, h, w), dtype=torch.float64, device=self.device)
+                     if plan.n_spatial > 1 else None)
+        self._work = _new_work(self.device)
+        self._pending = {}
+        self._next = 0
+        self._prev_end = 0
+        self._single = None
+
+    @property
+    def windows_done(self) -> int:
+        return self._next
+
+    def push_tile(self, k: int, disparity: torch.Tensor):
+        """disparity: fp32 CUDA [F, 480, 720] of tile k (any arrival order); completes windows in order."""
+        assert disparity.dtype == torch.float32 and disparity.device == self.device
+        self._pending[k] = disparity
+        ns = self.plan.n_spatial
+        while self._next < self.plan.n_temporal and all(self._next * ns + i in self._pending for i in range(ns)):
+            tiles = self.plan.tiles[self._next * ns:(self._next + 1) * ns]
+            self._push_window(tiles, [self._pending.pop(tl.k) for tl in tiles])
+            self._next += 1
+
+    def _push_window(self, tiles, disps):
+        p = self.plan
+        if p.n_spatial > 1:
+            rng = [(tl.w_start, tl.w_end) if p.is_horizontal else (tl.h_start, tl.h_end) for tl in tiles]
+            win = blend_chain(disps, rng, 2 if p.is_horizontal else 1, out=self._win, work=self._work)
+        else:
+            win = disps[0]
+        t0, t1 = tiles[0].t_start, tiles[0].t_end
+        if p.n_temporal == 1:
+            self._single = win.clone() if win is self._win else win     # dtype preserved like the reference (:262-264)
+        elif self._next == 0:
+            _scale_copy_(self.final[t0:t1], win, False)
+        else:
+            _append_(self.final, win, t0, self._prev_end, 0, self._work)
+        self._prev_end = t1
+
+    def result(self) -> torch.Tensor:
+        assert self._next == self.plan.n_temporal, "not every window has been pushed"
+        return self._single if self.plan.n_temporal == 1 else self.final
+
+
 def blend_all(disparities: Sequence[torch.Tensor], plan: Plan) -> torch.Tensor:
-    """Spatial blend inside each temporal window, then the temporal chain (reference order)."""
-    ns = plan.n_spatial
-    temporal, t_ranges = [], []
-    for ti in range(plan.n_temporal):
-        tl = plan.tiles[ti * ns:(ti + 1) * ns]
-        wins = [disparities[t.k] for t in tl]
-        rng = [(t.w_start, t.w_end) if plan.is_horizontal else (t.h_start, t.h_end) for t in tl]
-        temporal.append(blend_chain(wins, rng, 2 if plan.is_horizontal else 1))
-        t_ranges.append((tl[0].t_start, tl[0].t_end))
-    return blend_chain(temporal, t_ranges, 0)
+    """Spatial blend inside each temporal window, then the temporal chain (reference order), from a complete list."""
+    d0 = disparities[0]
+    t = max(tl.t_end for tl in plan.tiles)
+    h = max(tl.h_end for tl in plan.tiles)
+    w = max(tl.w_end for tl in plan.tiles)
+    sb = StreamingBlend(plan, t, h, w, d0.device)
+    for tl in plan.tiles:
+        sb.push_tile(tl.k, disparities[tl.k])
+    return sb.result()
+
+
+# ------------------------------------------------------------------------------------------ exchange step
+def exchange_round(round_tiles: Sequence[int], mine: Optional[Tuple[int, torch.Tensor]], shape, rank: int,
+                   world_size: int, root: int = 0, group=None, device=None) -> List[Tuple[int, torch.Tensor]]:
+    """Move the round's disparity tiles to the blend rank: every owner other than `root` sends its tile once, peer to
+    peer; `root` returns [(k, tile)] for all tiles of the round (its own included), the others return [].  A rank
+    without a tile in this round (last, partial round; or world_size > n_tiles) takes no part."""
+    if world_size == 1:
+        return [mine] if mine is not None else []
+    import torch.distributed as dist
+    ops, got = [], []
+    if rank == root:
+        for k in round_tiles:
+            if tile_owner(k, world_size) == root:
+                assert mine is not None and mine[0] == k
+                got.append(mine)
+            else:
+                buf = torch.empty(shape, dtype=torch.float32, device=device)
+                ops.append(dist.P2POp(dist.irecv, buf, tile_owner(k, world_size), group))
+                got.append((k, buf))
+    elif mine is not None:
+        ops.append(dist.P2POp(dist.isend, mine[1].contiguous(), root, group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    return sorted(got, key=lambda kv: kv[0]) if rank == root else []
 
 
 # ------------------------------------------------------------------------------------------ entry point
+class TileParallelRun:
+    """One sliding-window evaluation, driven round by round (`run_round(j)` for j in range(n_rounds), then
+    `finish()`).  `process_with_sliding_window` is the plain loop over it; bench.py times individual rounds."""
+
+    def __init__(self, pipeline, obs_image, num_inference_step: int, total_frames: int, seed: int, rank: int = 0,
+                 world_size: int = 1, group=None, device: Optional[torch.device] = None,
+                 tile_fn: Optional[Callable] = None, root: int = 0, skip_unused_rgb: bool = True,
+                 stats: Optional[dict] = None):
+        b, t, h, w, c = obs_image.shape
+        assert b == 1, "Only batch size 1 is supported"
+        self.pipeline, self.obs, self.steps, self.seed = pipeline, obs_image, num_inference_step, seed
+        self.rank, self.world, self.group, self.root = rank, world_size, group, root
+        self.tile_fn, self.skip_unused_rgb, self.stats = tile_fn, skip_unused_rgb, stats
+        self.plan = plan_windows(t, h, w, total_frames)
+        self.thw = (t, h, w)
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.n_tiles = len(self.plan.tiles)
+        tl0 = self.plan.tiles[0]
+        self.tile_shape = (self.plan.frames_per_window, tl0.h_end - tl0.h_start, tl0.w_end - tl0.w_start)
+        self.n_rounds = (self.n_tiles + world_size - 1) // world_size
+        with torch.cuda.device(self.device):
+            self.blend = StreamingBlend(self.plan, t, h, w, self.device) if rank == root else None
+        self.rgb0 = None
+        self._marks = []                                  # (kind, start_event, end_event)
+        self._fetched = 0
+
+    def _timed(self, kind, fn):
+        if self.stats is None:
+            return fn()
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        r = fn()
+        b_.record()
+        self._marks.append((kind, a, b_))
+        return r
+
+    def _run_tile(self, k):
+        tl = self.plan.tiles[k]
+        crop = self.obs[0, tl.t_start:tl.t_end, tl.h_start:tl.h_end, tl.w_start:tl.w_end, :]
+        if self.tile_fn is not None:
+            return self.tile_fn(tl, crop)
+        kw = {"decode_rgb": False} if (self.skip_unused_rgb and k != 0) else {}
+        out = self.pipeline(video=crop, num_inference_steps=self.steps, num_frames=tl.t_end - tl.t_start,
+                            generator=torch.Generator(device=self.device).manual_seed(self.seed), return_dict=False,
+                            fps=12, output_type="pt", **kw)
+        return (None if out[0] is None else out[0][0]), out[1][0]
+
+    def run_round(self, j: int):
+        """Round j: this rank's tile j * N + rank through the pipeline, the round's tiles to the blend rank, and (there)
+        every window that is now complete onto the chain.  Everything is enqueued on the current stream."""
+        with torch.cuda.device(self.device):
+            round_tiles = list(range(j * self.world, min((j + 1) * self.world, self.n_tiles)))
+            k = j * self.world + self.rank
+            mine = None
+            if k < self.n_tiles:
+                rgb, disp = self._timed("tile_ms", lambda: self._run_tile(k))
+                if k == 0:
+                    self.rgb0 = rgb
+                d = torch.as_tensor(disp).to(device=self.device, dtype=torch.float32)
+                assert tuple(d.shape) == self.tile_shape, (tuple(d.shape), self.tile_shape)
+                mine = (k, d)
+            got = self._timed("collective_ms", lambda: exchange_round(round_tiles, mine, self.tile_shape, self.rank,
+                                                                      self.world, self.root, self.group, self.device))
+            if self.rank == self.root:
+                self._timed("blend_ms", lambda: [self.blend.push_tile(kk, dd) for kk, dd in got])
+
+    def collect_stats(self):
+        """Fold the device timings recorded so far into `stats` (synchronises the device)."""
+        if self.stats is None:
+            return
+        torch.cuda.synchronize(self.device)
+        for kind, a, b_ in self._marks:
+            self.stats[kind] = self.stats.get(kind, 0.0) + a.elapsed_time(b_)
+        self._marks = []
+
+    def finish_stats_reset(self):
+        """Drop the timings recorded so far (e.g. after warm-up rounds)."""
+        if self.stats is not None:
+            torch.cuda.synchronize(self.device)
+            self._marks = []
+            self.stats.clear()
+
+    def fetch_finalized(self, out: Optional[torch.Tensor] = None):
+        """Blend rank, multi-window clips: the frames of the blended disparity that no later window can touch any more
+        (everything before the start of the next window to be pushed), copied to the host since the previous call --
+        lets a caller stream results out while later tiles are still being computed.  Returns (first_frame, numpy
+        fp64 [n, H, W]) or None when nothing new is final.  `out`: optional pinned host tensor to stage through."""
+        if self.blend is None or self.blend.final is None:
+            return None
+        m = self.blend.windows_done
+        upto = self.thw[0] if m >= self.plan.n_temporal else self.plan.tiles[m * self.plan.n_spatial].t_start
+        if m == 0 or upto <= self._fetched:
+            return None
+        lo, self._fetched = self._fetched, upto
+        src = self.blend.final[lo:upto]
+        if out is not None:
+            dst = out[: upto - lo]
+            dst.copy_(src, non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+            return lo, dst.numpy()
+        return lo, src.cpu().numpy()
+
+    def finish(self, result_on_all_ranks: bool = False, return_device: bool = False):
+        t, h, w = self.thw
+        plan, device = self.plan, self.device
+        with torch.cuda.device(device):
+            final = self.blend.result() if self.rank == self.root else None
+            rgb0 = self.rgb0
+            if self.world > 1 and result_on_all_ranks:
+                import torch.distributed as dist
+                dt = torch.float64 if (plan.n_temporal > 1 or plan.n_spatial > 1) else torch.float32
+                if self.rank != self.root:
+                    final = torch.empty((t, h, w), dtype=dt, device=device)
+                dist.broadcast(final, src=self.root, group=self.group)
+                r = (torch.as_tensor(np.asarray(rgb0) if not isinstance(rgb0, torch.Tensor) else rgb0,
+                                     dtype=torch.float32, device=device) if self.rank == self.root
+                     else torch.empty(self.tile_shape + (3,), dtype=torch.float32, device=device))
+                dist.broadcast(r, src=self.root, group=self.group)
+                rgb0 = r
+            out_rgb = out_disp = None
+            if final is not None:
+                def fetch():
+                    rr = rgb0.cpu().numpy() if isinstance(rgb0, torch.Tensor) else np.asarray(rgb0)
+                    return rr, (final if return_device else final.cpu().numpy())
+                out_rgb, out_disp = self._timed("d2h_ms", fetch)
+            if self.stats is not None:
+                self.collect_stats()
+                self.stats["tiles_run"] = len(partition_tiles(self.n_tiles, self.rank, self.world))
+                self.stats["rounds"] = self.n_rounds
+        return out_rgb, out_disp
+
+
 def process_with_sliding_window(pipeline, obs_image: np.ndarray, num_inference_step: int, total_frames: int,
                                 seed: int, rank: int = 0, world_size: int = 1, group=None,
                                 device: Optional[torch.device] = None,
-                                tile_fn: Optional[Callable] = None):
+                                tile_fn: Optional[Callable] = None, root: int = 0, result_on_all_ranks: bool = False,
+                                skip_unused_rgb: bool = True, stats: Optional[dict] = None,
+                                return_device: bool = False):
     """Same positional signature as the reference (launch_aether.py:81-83); rank/world_size/group select the
-    tile-parallel mode.  `tile_fn(tile, crop) -> (rgb, disparity)` overrides the pipeline call (tests)."""
-    b, t, h, w, c = obs_image.shape
-    assert b == 1, "Only batch size 1 is supported"
-    plan = plan_windows(t, h, w, total_frames)
-    device = device or torch.device("cuda", torch.cuda.current_device())
-    local = []
-    rgb0 = None
-    for k in partition_tiles(len(plan.tiles), rank, world_size):
-        tl = plan.tiles[k]
-        crop = obs_image[0, tl.t_start:tl.t_end, tl.h_start:tl.h_end, tl.w_start:tl.w_end, :]
-        if tile_fn is not None:
-            rgb, disp = tile_fn(tl, crop)
-        else:
-            rgb, disp, _ = pipeline(video=crop, num_inference_steps=num_inference_step, num_frames=tl.t_end - tl.t_start,
-                                    generator=torch.Generator(device=device).manual_seed(seed), return_dict=False,
-                                    fps=12)
-            rgb, disp = rgb[0], disp[0]
-        if k == 0:
-            rgb0 = rgb
-        d = torch.as_tensor(disp)
-        local.append((k, d.to(device=device, dtype=torch.float32)))
-    disparities = gather_tiles(local, len(plan.tiles), rank, world_size, group)
-    final = blend_all(disparities, plan)
-    if world_size > 1:
-        import torch.distributed as dist
-        shape = (plan.tiles[0].t_end - plan.tiles[0].t_start, plan.tiles[0].h_end - plan.tiles[0].h_start,
-                 plan.tiles[0].w_end - plan.tiles[0].w_start, 3)
-        r = torch.as_tensor(rgb0, dtype=torch.float32, device=device) if rank == 0 else torch.empty(
-            shape, dtype=torch.float32, device=device)
-        dist.broadcast(r, src=0, group=group)
-        rgb0 = r.cpu().numpy()
-    return np.asarray(rgb0), final.cpu().numpy()
+    tile-parallel mode.  `tile_fn(tile, crop) -> (rgb, disparity)` overrides the pipeline call (tests).
+    `skip_unused_rgb`: the reference decodes the rgb latents of every tile and keeps only those of tile 0
+    (:173-176, :265-266); with this flag the other tiles skip that VAE decode (identical outputs).
+    `stats` (optional dict) receives device-timed `tile_ms`, `collective_ms` (peer-to-peer exchange incl. the wait for
+    the slowest rank of each round), `blend_ms`, `d2h_ms` of this rank.
+    `return_device`: return the blended disparity as a CUDA fp64 tensor instead of numpy.
+    Returns (final_rgb, final_disparity) on the blend rank `root`; (None, None) elsewhere unless
+    `result_on_all_ranks`."""
+    run = TileParallelRun(pipeline, obs_image, num_inference_step, total_frames, seed, rank, world_size, group, device,
+                          tile_fn, root, skip_unused_rgb, stats)
+    for j in range(run.n_rounds):
+        run.run_round(j)
+    return run.finish(result_on_all_ranks, return_device)
 
 
 # ------------------------------------------------------------------------------------------ launcher glue (host side)
@@ -261,10 +487,15 @@ def disparity_to_depth(disparity: np.ndarray) -> np.ndarray:
 
 
 def evaluate_sequence(pipeline, frames: Sequence[np.ndarray], num_inference_step: int, seed: int, rank: int = 0,
-                      world_size: int = 1, group=None, device: Optional[torch.device] = None):
+                      world_size: int = 1, group=None, device: Optional[torch.device] = None, **kw):
     """One sequence of the video-depth evaluation (launch_aether.py:338-347) with the tiles spread over `world_size`
-    ranks: frames -> prepare_frames -> sliding-window inference + blend -> (rgb of tile 0, disparity, depth)."""
+    ranks: frames -> prepare_frames -> sliding-window inference + blend -> (rgb of tile 0, disparity, depth) on the
+    blend rank ((None, None, None) elsewhere).  depth = clip(1 / disparity, 0, 100) is taken on the device."""
     obs = prepare_frames(frames)[None]
     rgb, disparity = process_with_sliding_window(pipeline, obs, num_inference_step, len(frames), seed, rank=rank,
-                                                 world_size=world_size, group=group, device=device)
-    return rgb, disparity, disparity_to_depth(disparity)
+                                                 world_size=world_size, group=group, device=device,
+                                                 return_device=True, **kw)
+    if disparity is None:
+        return None, None, None
+    depth = disparity_to_depth_device(disparity)
+    return rgb, disparity.cpu().numpy(), depth.cpu().numpy()

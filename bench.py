@@ -1,26 +1,39 @@
 #!/usr/bin/env python
-"""bench.py -- headline metric of BASELINE.json: latent-frames/sec for a 41x480x720 50-step generation.
+"""bench.py -- headline metric of BASELINE.json: latent-frames/sec for a 41x480x720 50-step generation at 1/2/4/8 B200,
+measured on the path `north_star` shards: the tile-parallel sliding-window evaluation.
 
     python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torch.distributed.run)
     python bench.py --impl reference --gpus N --steps K --warmup W
 
-Workload = BASELINE.json configs[1] (reconstruction: 41 frames 480x720 -> 11 latent frames of 60x90,
-S = 226 + 14850 = 15076 tokens, 50 DPM steps, guidance 1.0 => batch 1, bf16), synthetic seeded weights of the
-full AetherV1 / CogVideoX-5b geometry (42 layers, 48 x 64, 5.55 B parameters) and synthetic latents.
+Workload.  A synthetic clip in the geometry of BASELINE.json configs[4] (480 x 853 frames -> two 480 x 720 spatial
+tiles per 41-frame temporal window, stride 8; reference evaluation/video_depth/launch_aether.py:81-287) is evaluated by
+`aether_b200.sliding_window.TileParallelRun`.  Its tiles are dealt round-robin over the N ranks and processed in
+ROUNDS; one bench "step" = one round:
 
-A "step" is one pass of the denoise-loop body (reference aetherv1_pipeline_cogvideox.py:827-921): 96-channel
-concat -> DiT forward (aether_dit_forward) -> fused CFG/DPM-Solver++ step (aether_cfg_dpm_step).  One 50-step
-generation yields 11 latent frames, so  value = N_gpus * 11 * (K / 50) / seconds.
-  value : inputs resident in HBM, CUDA-event time over exactly K steps, max over ranks.
-  e2e   : the public API end to end: AetherV1PipelineCogVideoX.__call__(task="reconstruction", 41x480x720, 50
-          steps) with a HOST numpy video in and HOST numpy rgb/disparity/raymap out -- preprocessing, H2D, VAE
-          encode, the loop, 2x VAE decode and D2H inside the timed region (value = N * 11 / seconds per call);
-          `denoise_step_pinned_host` additionally reports the bare step with pinned host buffers.
-  roofline : the attention kernel (dominant), duration from CUDA events recorded around every attention launch
-          on the launching stream inside the timed region; algorithmic flop = 4*B*H*S^2*64 per launch.
-  cpu_baseline / --impl reference : the reference's CPU path for this loop = the fp32 torch restatement of the
-          diffusers modules (oracle/), timed on the host cores on a bounded sample (one transformer block of one
-          forward at full S plus embed/tail) and extrapolated x42 layers x50 steps.
+    every rank runs ONE tile = one configs[1] generation (reconstruction, 41 frames 480x720 -> 11x60x90 latents,
+    S = 15076 tokens, 50 DPM steps, batch 1, bf16) through the full AetherV1PipelineCogVideoX.__call__ (VAE encode,
+    50 x (DiT forward + fused CFG/DPM step), rgb + disparity VAE decodes), the round's N - 1 remote disparity tiles
+    travel peer to peer (NCCL over NVLink) to the blend rank, and the blend chain there (spatial cross-fade + temporal
+    chain with the masked-LSQ scale, K10 kernels) advances by the windows that became complete.
+
+At N = 1 a step is therefore exactly one configs[1] generation (plus its share of the blend); the clip grows with N
+(one tile per rank per round) => "scaling": "weak"; value = N * 11 latent frames * K / seconds.
+  value : tile crops already resident in HBM, CUDA events around exactly K rounds, max over ranks.
+  e2e   : the same round with HOST buffers: the crop is host numpy float64 (what the reference's prepare_input hands
+          over, launch_aether.py:388-403), uploaded inside the timed region, and the frames of the blended disparity
+          that became final in the round are copied back to host numpy.
+  collective_ms / blend_ms : device-timed inside the timed rounds (blend rank), reported per round.
+  config5_4step : the reference's own evaluation setting (4 denoise steps per tile, launch_aether.py:67-70) on a
+          FIXED 8-tile clip at every N (strong scaling): seconds for the whole evaluate (tiles + exchange + blend +
+          D2H), with the exchange / blend / D2H parts separated -- the regime where the VAE and the blend matter.
+  roofline : the attention kernel (dominant), duration from CUDA events recorded around every attention launch on
+          the launching stream inside the timed region; algorithmic flop = 4*B*H*S^2*64 per launch.
+  gpu_library_baseline (N = 1): the same DiT forward through stock PyTorch (bf16 oracle modules on the GPU: cuDNN /
+          flash SDPA + cuBLAS + eager elementwise kernels) -- what the reference's diffusers path would execute on this
+          B200; outside the timed region, for context.
+  cpu_baseline / --impl reference : the reference's CPU path = the fp32 torch restatement of the diffusers modules
+          (oracle/), timed on the host cores on a bounded sample (two transformer blocks of one forward at full S plus
+          embed/tail, median of three samples) and extrapolated x42 layers x50 steps.
 """
 from __future__ import annotations
 
@@ -42,7 +55,12 @@ TEXT_LEN, TEXT_DIM = 226, 4096
 HEADS, LAYERS = 48, 42
 S_TOKENS = TEXT_LEN + LATENT_FRAMES * (LAT_H // 2) * (LAT_W // 2)
 DENOISE_STEPS = 50
-WORKLOAD = "configs[1]: reconstruction, 41 frames 480x720 -> 11x60x90 latents, S=15076, 50 steps, batch 1 (no CFG)"
+CLIP_H, CLIP_W, WINDOW, STRIDE_T = 480, 853, 41, 8
+METRIC = "latent-frames/sec, 41x480x720 50-step generation (tile-parallel sliding-window evaluation)"
+WORKLOAD = ("sliding-window evaluation rounds (configs[4] geometry: 480x853 clip, 2 spatial tiles x 41-frame windows, "
+            "stride 8); per round every rank runs one configs[1] tile (reconstruction, 41 frames 480x720 -> 11x60x90 "
+            "latents, S=15076, 50 steps, batch 1) through the full pipeline, NCCL p2p exchange to the blend rank, "
+            "blend chain advance")
 
 
 def _peaks():
@@ -97,70 +115,149 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU reference
-def cpu_reference_sample(threads: int, n_samples: int = 1):
-    """One transformer block (+ embed and tail) of one forward at full S on the host cores, fp32 oracle."""
+def _physical_cores() -> int:
+    try:
+        import psutil
+        n = psutil.cpu_count(logical=False)
+        if n:
+            return int(n)
+    except Exception:
+        pass
+    return os.cpu_count() or 1
+
+
+def cpu_reference_sample(n_samples: int = 3, k_layers: int = 2):
+    """k transformer blocks (+ embed and tail) of one forward at full S on the host cores, fp32 oracle.  One thread per
+    PHYSICAL core (SMT siblings only add noise to an fp32 GEMM), affinity left to the OS, median over the samples."""
     import torch
     from oracle.dit import DiTConfig, OracleDiT
     from oracle.rope import prepare_rotary_positional_embeddings
+    threads = _physical_cores()
     torch.set_num_threads(threads)
-    cfg = DiTConfig(num_layers=1)
+    cfg = DiTConfig(num_layers=k_layers)
     torch.manual_seed(0)
     model = OracleDiT(cfg).eval()
     x = torch.randn(1, LATENT_FRAMES, 96, LAT_H, LAT_W)
     e = torch.randn(1, TEXT_LEN, TEXT_DIM) * 0.2
     cos, sin = prepare_rotary_positional_embeddings(480, 720, LATENT_FRAMES)
     ts = torch.tensor([999])
-    times_full, times_nolayer = [], []
+    full, rest = [], []
     with torch.no_grad():
+        model(x, e, ts, image_rotary_emb=(cos, sin), n_layers=0)          # page in / thread-pool warm-up, untimed
         for _ in range(n_samples):
             t0 = time.perf_counter()
             model(x, e, ts, image_rotary_emb=(cos, sin))
-            times_full.append(time.perf_counter() - t0)
+            full.append(time.perf_counter() - t0)
             t0 = time.perf_counter()
             model(x, e, ts, image_rotary_emb=(cos, sin), n_layers=0)
-            times_nolayer.append(time.perf_counter() - t0)
-    t_full, t_rest = min(times_full), min(times_nolayer)
-    t_layer = max(t_full - t_rest, 1e-9)
+            rest.append(time.perf_counter() - t0)
+    t_full, t_rest = statistics.median(full), statistics.median(rest)
+    t_layer = max(t_full - t_rest, 1e-9) / k_layers
     t_forward = LAYERS * t_layer + t_rest
     value = LATENT_FRAMES / (DENOISE_STEPS * t_forward)
     return dict(value=value, t_layer_s=t_layer, t_embed_tail_s=t_rest, t_forward_extrapolated_s=t_forward,
-                cpu_work_s=sum(times_full) + sum(times_nolayer))
+                threads=threads, samples_s=[round(v, 3) for v in full], k_layers=k_layers,
+                cpu_work_s=sum(full) + sum(rest))
 
 
-def cpu_baseline_dict(r, threads, kind="port"):
-    return {"value": r["value"], "unit": "latent-frames/s", "cores": threads, "kind": kind,
-            "sample": (f"1 of {LAYERS} transformer blocks + embed/tail of ONE forward at full S={S_TOKENS} "
-                       f"(fp32 torch restatement of the diffusers modules, {r['t_layer_s']:.2f} s/block), "
-                       f"extrapolated x{LAYERS} layers x{DENOISE_STEPS} steps; diffusers itself is not installable here")}
+def cpu_baseline_dict(r, kind="port"):
+    return {"value": r["value"], "unit": "latent-frames/s", "cores": r["threads"], "kind": kind,
+            "sample": (f"{r['k_layers']} of {LAYERS} transformer blocks + embed/tail of ONE forward at full S={S_TOKENS} "
+                       f"(fp32 torch restatement of the diffusers modules; {len(r['samples_s'])} samples {r['samples_s']} s, "
+                       f"median -> {r['t_layer_s']:.2f} s/block on {r['threads']} threads = physical cores), extrapolated "
+                       f"x{LAYERS} layers x{DENOISE_STEPS} steps; VAE and blend of the round NOT included (favours the CPU "
+                       f"arm); diffusers itself is not installable here")}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    n = max(1, min(args.steps, 3))
-    r = cpu_reference_sample(threads, n_samples=n)
-    ms_per_step = r["t_forward_extrapolated_s"] * 1000.0
-    line = {"impl": "reference", "metric": "latent-frames/sec, 41x480x720 50-step generation (denoise loop)",
-            "value": r["value"], "unit": "latent-frames/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "device": "host CPU", "samples_timed": n},
-            "cpu_baseline": cpu_baseline_dict(r, threads),
+    r = cpu_reference_sample(n_samples=3, k_layers=2)
+    ms_per_step = r["t_forward_extrapolated_s"] * DENOISE_STEPS * 1000.0          # one round = one 50-step generation
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "latent-frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "device": "host CPU", "samples_timed": len(r["samples_s"]),
+                       "extrapolated": True},
+            "cpu_baseline": cpu_baseline_dict(r),
             "e2e": {"value": r["value"], "unit": "latent-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------ product arm
+class SyntheticClip:
+    """Stands in for the [1, T, H, W, 3] float64 array of launch_aether.prepare_input without holding T x 9.8 MB of
+    host memory: crops are generated per tile, seeded by the tile position, either resident on the device (float32,
+    `value` rounds) or as host numpy float64 (`e2e` rounds)."""
+
+    def __init__(self, t, h, w, device):
+        self.shape = (1, t, h, w, 3)
+        self.device = device
+        self.host_mode = False
+        self._cache = {}
+
+    def __getitem__(self, idx):
+        import numpy as np
+        import torch
+        _, ts, hs, ws, _ = idx
+        n, hh, ww = ts.stop - ts.start, hs.stop - hs.start, ws.stop - ws.start
+        seed = ts.start * 1000 + ws.start
+        if self.host_mode:
+            return np.random.default_rng(seed).random((n, hh, ww, 3))                     # float64 in [0, 1)
+        key = (n, hh, ww)
+        if key not in self._cache:      # one resident crop per shape: "inputs already resident in HBM"
+            g = torch.Generator(device=self.device).manual_seed(seed)
+            self._cache[key] = torch.rand((n, hh, ww, 3), device=self.device, generator=g, dtype=torch.float32)
+        return self._cache[key]
+
+
+def clip_frames_for_tiles(n_tiles: int) -> int:
+    n_windows = (n_tiles + 1) // 2
+    return WINDOW + STRIDE_T * (n_windows - 1)
+
+
+def gpu_library_forward_ms(dev, reps: int = 3):
+    """One DiT forward at the bench shape through stock PyTorch (oracle modules in bf16 on the GPU)."""
+    import torch
+    from oracle.dit import DiTConfig, OracleDiT
+    from oracle.rope import prepare_rotary_positional_embeddings
+    with torch.device(dev):
+        model = OracleDiT(DiTConfig()).to(torch.bfloat16).eval()
+    g = torch.Generator(device=dev).manual_seed(0)
+    with torch.no_grad():
+        for p in model.parameters():
+            p.copy_(torch.randn(p.shape, device=dev, generator=g, dtype=torch.float32) * 0.02)
+    x = torch.randn(1, LATENT_FRAMES, 96, LAT_H, LAT_W, device=dev, generator=g).bfloat16()
+    e = (torch.randn(1, TEXT_LEN, TEXT_DIM, device=dev, generator=g) * 0.2).bfloat16()
+    cos, sin = prepare_rotary_positional_embeddings(480, 720, LATENT_FRAMES)
+    cos, sin = cos.to(dev), sin.to(dev)
+    ts = torch.tensor([999], device=dev)
+    times = []
+    with torch.no_grad():
+        for i in range(reps + 1):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            model(x, e, ts, image_rotary_emb=(cos, sin))
+            b.record()
+            torch.cuda.synchronize()
+            if i:
+                times.append(a.elapsed_time(b))
+    del model
+    torch.cuda.empty_cache()
+    return statistics.median(times)
+
+
 def run_product(args):
+    import numpy as np
     import torch
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
@@ -168,130 +265,119 @@ def run_product(args):
     from aether_b200 import _lib
     if not _lib.lib_path().exists():
         ge.build()
-    from aether_b200.rope import prepare_rotary_positional_embeddings
+    from aether_b200.pipeline import AetherV1PipelineCogVideoX
     from aether_b200.scheduler import AetherDPMScheduler
+    from aether_b200.sliding_window import TileParallelRun, process_with_sliding_window
     from aether_b200.transformer import AetherTransformer3D
+    from aether_b200.vae import AetherVAE
 
     model = AetherTransformer3D(device=dev)
     model.init_synthetic_(seed=0)
     model.pack(release_unpacked=True)
-    sched = AetherDPMScheduler()
-    sched.set_timesteps(DENOISE_STEPS, device=dev)
-    t_host = [int(v) for v in sched.timesteps.tolist()]
-    g = torch.Generator(device=dev).manual_seed(42 + rank)
-    latents = torch.randn(1, LATENT_FRAMES, 56, LAT_H, LAT_W, device=dev, generator=g, dtype=torch.bfloat16)
-    cond = (torch.randn(1, LATENT_FRAMES, 40, LAT_H, LAT_W, device=dev, generator=g) * 0.7).to(torch.bfloat16)
-    text = (torch.randn(1, TEXT_LEN, TEXT_DIM, device=dev, generator=g) * 0.2).to(torch.bfloat16)
-    rope = prepare_rotary_positional_embeddings(480, 720, LATENT_FRAMES, patch_size=2, vae_scale_factor_spatial=8,
-                                                sample_height=60, sample_width=90, attention_head_dim=64,
-                                                base_fps=12, fps=12, device=dev)
-    noise_gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    state = {"latents": latents, "old": None}
-
-    def step(i, lat_in=None):
-        k = i % DENOISE_STEPS
-        if k == 0:
-            state["old"] = None
-        lat = state["latents"] if lat_in is None else lat_in
-        # the 96-channel concat of reference :857 happens inside the patch-gather kernel (aether_dit_forward_split)
-        out = model.forward_split(lat, cond, text, sched.timesteps[k].reshape(1), rope)
-        new, state["old"] = sched.step_fused(out, 1.0, state["old"], t_host[k], t_host[k - 1] if k > 0 else None, lat,
-                                             generator=noise_gen)
-        state["latents"] = new
-        return new
+    vae = AetherVAE(device=dev)
+    vae.init_synthetic_(seed=1)
+    vae.enable_slicing()
+    vae.enable_tiling()
+    text = torch.randn(1, TEXT_LEN, TEXT_DIM, generator=torch.Generator().manual_seed(3)) * 0.2
+    pipe = AetherV1PipelineCogVideoX(vae=vae, scheduler=AetherDPMScheduler(), transformer=model,
+                                     empty_prompt_embeds=text).to(dev)
+    tile_steps = args.tile_steps
+    warmup = max(args.warmup, 3)
+    n_e2e = 1 + ((warmup + args.steps + 1) * world) % 2         # keeps the tile count even (two tiles per window)
+    rounds = warmup + args.steps + n_e2e
+    clip = SyntheticClip(clip_frames_for_tiles(rounds * world), CLIP_H, CLIP_W, dev)
+    stats = {}
+    # the evaluation decodes rgb for every tile like the reference (skip_unused_rgb=False): a round is a complete
+    # configs[1] generation, nothing of it is skipped
+    run = TileParallelRun(pipe, clip, tile_steps, clip.shape[1], seed=3407, rank=rank, world_size=world, device=dev,
+                          skip_unused_rgb=False, stats=stats)
+    assert run.n_rounds == rounds, (run.n_rounds, rounds)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(max(args.warmup, 3)):
-        step(i)
+    def max_over_ranks(ms):
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    calls0 = _lib.CALLS[0]
+    for j in range(warmup):
+        run.run_round(j)
+    torch.cuda.synchronize()
+    calls_per_round = (_lib.CALLS[0] - calls0) / warmup
+    run.finish_stats_reset()
+
+    # ---- timed region: exactly K rounds
     model.enable_timing(True)
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    attn_ms = attn_n = 0
     ev0.record()
-    for i in range(args.steps):
-        step(i)
-    ev1.record()
+    for j in range(warmup, warmup + args.steps):
+        run.run_round(j)
+        if j == warmup + args.steps - 1:
+            ev1.record()
+        torch.cuda.current_stream().synchronize()         # the host loop of the evaluation is synchronous per tile
+        ms, n = model.read_attention_timing()             # attention launches of the round's last denoise step
+        attn_ms, attn_n = attn_ms + ms, attn_n + n
     barrier()
-    elapsed_ms = ev0.elapsed_time(ev1)
+    elapsed_ms = max_over_ranks(ev0.elapsed_time(ev1))
     clocks = sampler.stop() if sampler else None
-    attn_ms, attn_n = model.read_attention_timing()
     model.enable_timing(False)
-    tmax = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(tmax.item())
-    value = world * LATENT_FRAMES * (args.steps / DENOISE_STEPS) / (elapsed_ms / 1000.0)
+    run.collect_stats()
+    timed_stats = dict(stats)
+    run.finish_stats_reset()
+    value = world * LATENT_FRAMES * args.steps * (tile_steps / DENOISE_STEPS) / (elapsed_ms / 1000.0)
 
-    # ---- e2e: same step, pinned host buffers in the timed region
-    n_e2e = max(1, min(args.steps, 10))
-    host_in = torch.empty(1, LATENT_FRAMES, 56, LAT_H, LAT_W, dtype=torch.bfloat16).pin_memory()
-    host_cond = cond.cpu().pin_memory()
-    host_out = torch.empty_like(host_in).pin_memory()
-    host_in.copy_(state["latents"].cpu())
-    dev_in = torch.empty_like(latents)
-    h2d = host_in.numel() * 2 + host_cond.numel() * 2
-    d2h = host_out.numel() * 2
+    # ---- e2e: the same round with host buffers (host float64 crop in, finalised blended frames out)
+    clip.host_mode = True
+    pinned = (torch.empty((WINDOW + STRIDE_T * world, CLIP_H, CLIP_W), dtype=torch.float64).pin_memory()
+              if rank == 0 else None)
+    run.fetch_finalized(pinned)                            # frames finalised before the e2e rounds are not counted
+    h2d = WINDOW * 480 * 720 * 3 * 8
+    d2h = 0
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(n_e2e):
-        dev_in.copy_(host_in, non_blocking=True)
-        cond.copy_(host_cond, non_blocking=True)
-        new = step(i, dev_in)
-        host_out.copy_(new, non_blocking=True)
-        torch.cuda.current_stream().synchronize()      # the caller consumes the step result on the host
-        host_in.copy_(host_out)
-    e1.record()
-    barrier()
-    e2e_ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_step_value = world * LATENT_FRAMES * (n_e2e / DENOISE_STEPS) / (float(e2e_ms.item()) / 1000.0)
-    e2e = {"value": e2e_step_value, "unit": "latent-frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "steps": n_e2e, "scope": "denoise step via the public modules with pinned host buffers; VAE not included"}
+    t0 = time.perf_counter()
+    for j in range(warmup + args.steps, rounds):
+        run.run_round(j)
+        got = run.fetch_finalized(pinned)
+        if got is not None:
+            d2h += got[1].nbytes
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks((time.perf_counter() - t0) * 1000.0) / 1000.0
+    e2e = {"value": world * LATENT_FRAMES * n_e2e * (tile_steps / DENOISE_STEPS) / e2e_s, "unit": "latent-frames/s",
+           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h / n_e2e), "seconds_per_round": e2e_s / n_e2e,
+           "rounds": n_e2e,
+           "scope": "one round through the public API with HOST buffers: host numpy float64 crop [41,480,720,3] -> "
+                    "AetherV1PipelineCogVideoX.__call__ (upload, preprocess, VAE encode, 50 x (DiT + DPM step), rgb + "
+                    "disparity VAE decode) -> NCCL p2p exchange -> blend chain -> D2H of the frames finalised by the round "
+                    "(bytes per round, blend rank)"}
+    run.finish()                                           # complete the chain (last window already pushed)
+    clip.host_mode = False
 
-    # ---- e2e proper: the public API.  AetherV1PipelineCogVideoX.__call__ (reconstruction, 41 x 480 x 720, 50 steps)
-    # with a HOST numpy video in and HOST numpy rgb / disparity / raymap out: input preprocessing, H2D, VAE encode,
-    # the 50-step loop, 2 x VAE decode and D2H are all inside the timed region.
-    if not args.no_full_e2e:
-        import numpy as np
-        from aether_b200.pipeline import AetherV1PipelineCogVideoX
-        from aether_b200.vae import AetherVAE
-        vae = AetherVAE(device=dev)
-        vae.init_synthetic_(seed=1)
-        vae.enable_slicing()
-        vae.enable_tiling()
-        pipe = AetherV1PipelineCogVideoX(vae=vae, scheduler=AetherDPMScheduler(), transformer=model,
-                                         empty_prompt_embeds=text.cpu()).to(dev)
-        rng = np.random.default_rng(7 + rank)
-        video = rng.random((41, 480, 720, 3), dtype=np.float32)
-
-        def call(n):
-            return pipe(task="reconstruction", video=video, height=480, width=720, num_frames=41, fps=12,
-                        num_inference_steps=n, generator=torch.Generator(device=dev).manual_seed(42 + rank))
-
-        call(1)                                                     # warm-up call (VAE kernels, allocator)
+    # ---- configs[4] at its own setting (4 denoise steps per tile), fixed 8-tile clip at every N: strong scaling
+    strong = None
+    if not args.no_strong_leg:
+        sclip = SyntheticClip(clip_frames_for_tiles(8), CLIP_H, CLIP_W, dev)
+        sclip.host_mode = True
+        sstats = {}
         barrier()
         t0 = time.perf_counter()
-        out = call(DENOISE_STEPS)
+        _, disp = process_with_sliding_window(pipe, sclip, 4, sclip.shape[1], 3407, rank=rank, world_size=world,
+                                              device=dev, stats=sstats)
         torch.cuda.synchronize()
-        tc = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(tc, op=dist.ReduceOp.MAX)
-        t_call = float(tc.item())
-        e2e = {"value": world * LATENT_FRAMES / t_call, "unit": "latent-frames/s",
-               "h2d_bytes_per_step": int(video.size * 2),
-               "d2h_bytes_per_step": int(out.rgb.nbytes + out.disparity.nbytes + out.raymap.nbytes),
-               "seconds_per_call": t_call, "calls": 1,
-               "scope": "AetherV1PipelineCogVideoX.__call__(reconstruction, 41x480x720, 50 steps): host numpy video -> "
-                        "preprocess -> H2D -> VAE encode -> 50 x (DiT + DPM step) -> 2 x VAE decode -> D2H numpy outputs "
-                        "(bytes are per call)",
-               "denoise_step_pinned_host": {"value": e2e_step_value, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                                            "steps": n_e2e}}
+        s_s = max_over_ranks((time.perf_counter() - t0) * 1000.0) / 1000.0
+        strong = {"tiles": 8, "frames": sclip.shape[1], "denoise_steps_per_tile": 4, "seconds": s_s,
+                  "value": 8 * LATENT_FRAMES / s_s, "unit": "latent-frames/s (4-step tiles)", "scaling": "strong",
+                  "blend_rank_ms": {k: round(v, 3) for k, v in sstats.items() if k.endswith("_ms")},
+                  "scope": "evaluate one 65-frame 480x853 clip end to end (host float64 frames in, blended fp64 disparity "
+                           "out on the blend rank): 8 tiles over N ranks, rgb decode skipped for tiles whose rgb the "
+                           "reference discards"}
 
     if rank == 0:
         peak, peak_src = _peaks()
@@ -302,27 +388,59 @@ def run_product(args):
         prof = ROOT / "profiles" / "attention_traffic.json"
         if prof.exists():
             traffic = json.loads(prof.read_text()).get("dram_bytes_per_launch")
+        ms_per_step = elapsed_ms / args.steps
+        per_round = lambda k: round(timed_stats.get(k, 0.0) / args.steps, 3)
         line = {
-            "metric": "latent-frames/sec, 41x480x720 50-step generation (denoise loop)",
-            "value": value, "unit": "latent-frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "model": "AetherV1 DiT geometry (42 layers, 48x64, in 96 / out 56), seeded synthetic weights",
-                       "denoise_steps": DENOISE_STEPS, "tokens": S_TOKENS, "attention_mode": int(model.attention_fp16_pv),
-                       "parallelism": f"replicas x{world} (independent tiles per GPU, no data-path collective)",
+            "metric": METRIC, "value": value, "unit": "latent-frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD,
+                       "model": "AetherV1 DiT geometry (42 layers, 48x64, in 96 / out 56) + CogVideoX-5b VAE geometry, "
+                                "seeded synthetic weights",
+                       "denoise_steps": tile_steps, "tokens": S_TOKENS, "attention_mode": int(model.attention_fp16_pv),
+                       "tiles_per_round": world, "clip_frames": clip.shape[1],
+                       "parallelism": f"tile-parallel x{world}: round-robin tiles, NCCL p2p of the disparity tiles to the "
+                                      f"blend rank each round, streaming blend chain on rank 0",
                        "l2": "per-step working set (11.1 GB weights + ~1.4 GB activations) >> 126 MB L2; no explicit flush"},
             "e2e": e2e,
-            "gpu_launches": (model.launches_per_forward(1) + 1) * args.steps,
+            "collective_ms": per_round("collective_ms"), "blend_ms": per_round("blend_ms"),
+            "tile_ms": per_round("tile_ms"),
+            "collective_note": "per round on the blend rank; includes waiting for the slowest rank's tile of the round",
+            "gpu_launches": int(round(calls_per_round + tile_steps * (model.launches_per_forward(1) - 1))) * args.steps,
             "clocks": clocks,
-            "roofline": {"kernel": f"aether_attention_bf16 mode {int(model.attention_fp16_pv)} (tcgen05, attention_v3_kernel)",
+            "roofline": {"kernel": f"aether_attention_bf16 mode {int(model.attention_fp16_pv)} (tcgen05)",
                          "bound": "tensor", "achieved": achieved, "peak": peak,
                          "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                          "peak_source": peak_src, "launches_timed": attn_n, "avg_launch_ms": avg_ms,
-                         "share_of_step": attn_ms / (elapsed_ms / args.steps) if attn_n else None},
+                         "share_of_step": (avg_ms * LAYERS * tile_steps / ms_per_step) if attn_n else None},
         }
+        if tile_steps != DENOISE_STEPS:
+            line["config"]["INVALID_FOR_HEADLINE"] = f"--tile-steps {tile_steps} (development run; the metric needs 50)"
+        if strong is not None:
+            line["config5_4step"] = strong
+        if world == 1 and not args.no_gpu_library_baseline:
+            fwd_ms = gpu_library_forward_ms(dev)
+            line["gpu_library_baseline"] = {
+                "dit_forward_ms": fwd_ms, "ours_dit_forward_ms": None,
+                "what": "one CogVideoX DiT forward (B=1, S=15076, 42 layers) through stock PyTorch bf16 on this GPU "
+                        "(F.scaled_dot_product_attention + cuBLAS + eager elementwise): the device work the reference's "
+                        "diffusers path would launch; outside the timed region"}
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g = torch.Generator(device=dev).manual_seed(5)
+            lat = torch.randn(1, LATENT_FRAMES, 96, LAT_H, LAT_W, device=dev, generator=g).bfloat16()
+            rope = pipe._prepare_rotary_positional_embeddings(480, 720, LATENT_FRAMES, dev, fps=12)
+            tt = torch.tensor([999], device=dev)
+            ours = []
+            for i in range(4):
+                a.record()
+                model(lat, text.to(dev).bfloat16(), tt, image_rotary_emb=rope)
+                b.record()
+                torch.cuda.synchronize()
+                if i:
+                    ours.append(a.elapsed_time(b))
+            line["gpu_library_baseline"]["ours_dit_forward_ms"] = statistics.median(ours)
         if world == 1 and not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
-            line["cpu_baseline"] = cpu_baseline_dict(cpu_reference_sample(threads, 1), threads)
+            line["cpu_baseline"] = cpu_baseline_dict(cpu_reference_sample(3, 2))
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -332,11 +450,14 @@ def run_product(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
+    ap.add_argument("--tile-steps", type=int, default=DENOISE_STEPS,
+                    help="denoise steps per tile (development only; the headline metric is defined at 50)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-full-e2e", action="store_true", help="skip the full pipeline __call__ e2e measurement")
+    ap.add_argument("--no-gpu-library-baseline", action="store_true")
+    ap.add_argument("--no-strong-leg", action="store_true", help="skip the fixed-clip 4-step strong-scaling leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

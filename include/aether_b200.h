@@ -245,25 +245,33 @@ int aether_cfg_dpm_step(const void* model_out, int32_t model_out_fp32, int32_t n
 
 /* ---------------------------------------------------------------- sliding-window blend (K10) */
 
-/* All three work on a 3-D region [n0, n1, n2] (frames x rows x cols; strides s0, s1 in ELEMENTS, unit stride
+/* All of these work on a 3-D region [n0, n1, n2] (frames x rows x cols; strides s0, s1 in ELEMENTS, unit stride
  * on the last axis) of disparity buffers that are fp32 (a raw pipeline window) or fp64 (an already blended
  * accumulation; the reference's np.ones(float64) result buffers).
  *
- * aether_scale_reduce: out[0] += sum(f32(p)*f32(t)), out[1] += sum(f32(p)*f32(p)); out is fp64[2], zeroed by
- *   the caller; scale = out[0]/out[1] (0 when out[1] == 0) is compute_scale (postprocess_utils.py:847-864).
+ * aether_scale_reduce: work[0] = sum(f32(p)*f32(t)), work[1] = sum(f32(p)*f32(p)) as fp64 (deterministic two-stage
+ *   reduction); `work` is a device buffer of aether_scale_reduce_work_bytes() bytes, 8-byte aligned, ZEROED ONCE by
+ *   the caller when it is allocated (the kernel leaves its block counter at zero again).  scale = f32(work[0]) /
+ *   f32(work[1]) (0 when the denominator is 0) is compute_scale (postprocess_utils.py:847-864).
  * aether_blend_crossfade: dst = acc * w + (scale*win) * (1-w), w = np.linspace(1, 0, n_axis)[index along axis]
  *   (launch_aether.py:217-250 spatial, axis 2 or 1;  :281-284 temporal, axis 0)
- * aether_scale_copy: dst = apply_scale ? scale*src : src, widened to fp64   (launch_aether.py:220-227, :277-280) */
+ * aether_scale_copy: dst = apply_scale ? scale*src : src, widened to fp64   (launch_aether.py:220-227, :277-280)
+ *   Both take the scale either from the host (`scale`, scale_sums == NULL) or, without any host round trip, from
+ *   the device buffer a preceding aether_scale_reduce on the same stream filled (`scale_sums` = its `work`).
+ * aether_disparity_to_depth: dst(fp64) = clip(1 / src, 0, 100)   (launch_aether.py:347) */
+int64_t aether_scale_reduce_work_bytes(void);
 int aether_scale_reduce(const void* pred, int32_t pred_is_f64, int64_t pred_s0, int64_t pred_s1, const void* target,
                         int32_t target_is_f64, int64_t target_s0, int64_t target_s1, int64_t n0, int64_t n1,
-                        int64_t n2, double* out, void* stream);
+                        int64_t n2, void* work, void* stream);
 int aether_blend_crossfade(double* dst, int64_t dst_s0, int64_t dst_s1, const void* acc, int32_t acc_is_f64,
                            int64_t acc_s0, int64_t acc_s1, const void* win, int32_t win_is_f64, int64_t win_s0,
-                           int64_t win_s1, double scale, int64_t n0, int64_t n1, int64_t n2, int32_t axis,
-                           void* stream);
+                           int64_t win_s1, double scale, const double* scale_sums, int64_t n0, int64_t n1, int64_t n2,
+                           int32_t axis, void* stream);
 int aether_scale_copy(double* dst, int64_t dst_s0, int64_t dst_s1, const void* src, int32_t src_is_f64, int64_t src_s0,
-                      int64_t src_s1, double scale, int32_t apply_scale, int64_t n0, int64_t n1, int64_t n2,
-                      void* stream);
+                      int64_t src_s1, double scale, const double* scale_sums, int32_t apply_scale, int64_t n0,
+                      int64_t n1, int64_t n2, void* stream);
+int aether_disparity_to_depth(double* dst, int64_t dst_s0, int64_t dst_s1, const void* src, int32_t src_is_f64,
+                              int64_t src_s0, int64_t src_s1, int64_t n0, int64_t n1, int64_t n2, void* stream);
 
 #ifdef __cplusplus
 }

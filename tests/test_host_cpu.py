@@ -141,23 +141,36 @@ def _free_port():
 
 
 def _worker(rank, world, port, n_tiles, q):
+    """The exchange step of the tile-parallel sliding-window path on gloo: rounds of one tile per rank, every
+    non-root owner sends its tile once to the blend rank, which must see every tile exactly once, in order."""
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     sys.path.insert(0, str(ROOT))
-    from aether_b200.sliding_window import gather_tiles, partition_tiles
+    from aether_b200.sliding_window import exchange_round, partition_tiles, tile_owner
     mine = partition_tiles(n_tiles, rank, world)
-    local = [(k, torch.full((3, 4, 5), float(k)) + torch.arange(5.0)) for k in mine]
-    full = gather_tiles(local, n_tiles, rank, world)
-    ok = all(torch.equal(full[k], torch.full((3, 4, 5), float(k)) + torch.arange(5.0)) for k in range(n_tiles))
+    make = lambda k: torch.full((3, 4, 5), float(k)) + torch.arange(5.0)
+    seen = []
+    for j in range((n_tiles + world - 1) // world):
+        round_tiles = list(range(j * world, min((j + 1) * world, n_tiles)))
+        k = j * world + rank
+        own = (k, make(k)) if k < n_tiles else None
+        assert (own is not None) == (k in mine) and all(tile_owner(t, world) == t % world for t in round_tiles)
+        got = exchange_round(round_tiles, own, (3, 4, 5), rank, world, root=0, device=torch.device("cpu"))
+        if rank == 0:
+            assert [kk for kk, _ in got] == round_tiles
+            seen += [(kk, torch.equal(d, make(kk))) for kk, d in got]
+        else:
+            assert got == []
+    ok = (seen == [(k, True) for k in range(n_tiles)]) if rank == 0 else True
     q.put((rank, ok, len(mine)))
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_tiles", [7, 4])
-def test_gather_tiles_gloo_world2(n_tiles):
+@pytest.mark.parametrize("n_tiles", [7, 4, 1])          # 1 tile on 2 ranks: a rank with no work must not hang the job
+def test_exchange_rounds_gloo_world2(n_tiles):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()

@@ -1,6 +1,7 @@
-"""Tile-parallel sliding-window path on N GPUs (torchrun, NCCL): every rank runs its share of the tiles, ONE
-all-gather over NVLink exchanges the disparity tiles, every rank blends on its device and checks the result
-against the reference's golden blend (tests/golden/sliding_*.npz).
+"""Tile-parallel sliding-window path on N GPUs (torchrun, NCCL): every rank runs its share of the tiles in rounds, the
+disparity tiles of each round travel peer to peer over NVLink to the blend rank, which streams them onto the chain; the
+result (broadcast back for this check) is compared on every rank with the reference's golden blend
+(tests/golden/sliding_*.npz).
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
         tools/multigpu_sliding.py
@@ -37,7 +38,9 @@ def main():
             return fake_tile_outputs(crop, tl.t_start, tl.h_start, tl.w_start)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        rgb, disp = process_with_sliding_window(None, obs, 4, t, 3407, rank=rank, world_size=world, tile_fn=tile_fn)
+        stats = {}
+        rgb, disp = process_with_sliding_window(None, obs, 4, t, 3407, rank=rank, world_size=world, tile_fn=tile_fn,
+                                                result_on_all_ranks=True, stats=stats)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         n_tiles = len(plan_windows(t, h, w, t).tiles)
@@ -47,7 +50,7 @@ def main():
                 and ran == list(range(rank, n_tiles, world)))
         ok = ok and good
         print(f"[rank {rank}/{world}] sliding_{name}: tiles run here {ran} of {n_tiles}; matches reference golden: {good}; "
-              f"{dt:.2f} s", flush=True)
+              f"{dt:.2f} s; device-timed ms {dict((k, round(v, 2)) for k, v in stats.items())}", flush=True)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
