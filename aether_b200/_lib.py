@@ -39,6 +39,21 @@ class DitWeights(C.Structure):
         "pos_embedding")] + [("layers", C.POINTER(DitLayerWeights))]
 
 
+class VaeConfig(C.Structure):
+    _fields_ = [("in_channels", c_int32), ("out_channels", c_int32), ("latent_channels", c_int32),
+                ("num_blocks", c_int32), ("layers_per_block", c_int32), ("norm_num_groups", c_int32),
+                ("norm_eps", c_float), ("temporal_compression_ratio", c_int32), ("use_tiling", c_int32),
+                ("num_latent_frames_batch_size", c_int32), ("num_sample_frames_batch_size", c_int32),
+                ("tile_sample_min_height", c_int32), ("tile_sample_min_width", c_int32),
+                ("tile_latent_min_height", c_int32), ("tile_latent_min_width", c_int32)] + [
+        (f"{s}_{k}_{a}", c_int32) for s in ("enc", "dec") for k in ("overlap", "blend", "limit") for a in ("h", "w")]
+
+
+class VaeParam(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("kind", c_int32), ("data", c_void_p), ("bias", c_void_p), ("kt", c_int32),
+                ("kh", c_int32), ("kw", c_int32), ("cin", c_int32), ("cout", c_int32)]
+
+
 class DpmCoeffs(C.Structure):
     _fields_ = [("sqrt_alpha", c_float), ("sqrt_one_minus_alpha", c_float), ("m1", c_float), ("m2", c_float),
                 ("m3", c_float), ("m4", c_float), ("m_noise", c_float), ("second_order", c_int32),
@@ -95,6 +110,15 @@ SIGNATURES = {
     "aether_posterior_sample": (C.c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_int64, c_void_p]),
     "aether_tile_blend": (C.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
                                     c_int32, c_void_p]),
+    "aether_vae_create": (C.c_int, [C.POINTER(VaeConfig), C.POINTER(VaeParam), c_int32, C.POINTER(c_void_p)]),
+    "aether_vae_destroy": (None, [c_void_p]),
+    "aether_vae_workspace_bytes": (c_int64, [c_void_p, c_int32, c_int32, c_int32, c_int32]),
+    "aether_vae_launch_count": (c_int64, [c_void_p, c_int32, c_int32, c_int32, c_int32]),
+    "aether_vae_output_shape": (C.c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, C.POINTER(c_int32)]),
+    "aether_vae_encode": (C.c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32, c_int32, c_int32, c_void_p,
+                                    c_void_p, c_int64, c_void_p]),
+    "aether_vae_decode": (C.c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32, c_int32, c_int32, c_void_p,
+                                    c_void_p, c_int64, c_void_p]),
     "aether_cfg_dpm_step": (C.c_int, [c_void_p, c_int32, c_int32, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
                                       C.POINTER(DpmCoeffs), c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "aether_scale_reduce_work_bytes": (c_int64, []),

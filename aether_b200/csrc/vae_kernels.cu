@@ -5,6 +5,7 @@
 // 16-byte vectors (8 channels per thread).  Algorithmic bytes are noted per kernel.
 #include "host_util.h"
 #include "ptx.cuh"
+#include "vae_internal.h"
 
 namespace aether {
 
@@ -121,67 +122,76 @@ struct GnApplyArgs {
   const float* beta;
   const __nv_bfloat16* zy;     // nullable: [Tz, hz, wz, C]
   const __nv_bfloat16* zb;
-  const int* tmap;             // [T] frame -> latent frame (device)
   int H, W, hz, wz;
   int zld;                     // row stride (elements) of the zy / zb tables
   int silu;
 };
 
-__global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyArgs a) {
+// Work layout: a thread owns ONE 8-channel vector of the row for the whole launch, so its group statistics and
+// affine parameters (mean, rstd*gamma, beta: 24 registers) are fetched once; a block covers 256 / (C/8) consecutive
+// rows per pass and walks the tensor in a grid-stride loop over row groups with four independent 16-byte loads in
+// flight per thread.  Round 1 looked all of that up per element (8 mean/rstd pairs, 64 B of gamma/beta, an int64
+// division per vector, three more for the latent gather) and sat at 17 % of the copy bandwidth.
+// MapT: `const int*` (device array, the per-kernel C entry point) or `IMap` (by value, the handle-level executor).
+template <bool SPATIAL, class MapT>
+__global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyArgs a, const MapT tmap) {
   const int tpr = a.C / 8;
-  const int64_t total = a.N * tpr;
+  const int lane_c = threadIdx.x % tpr;
+  const int row_in_blk = threadIdx.x / tpr;
+  const int rows_per_blk = 256 / tpr;
+  const int c0 = lane_c * 8;
   const int gs = a.C / a.G;
-  const int64_t gstride = int64_t(gridDim.x) * blockDim.x;
-  for (int64_t i0 = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i0 < total; i0 += 4 * gstride) {
-    uint4 xin[4];                     // 4 independent 16-byte loads in flight before any dependent work / store
+  float mu[8], sc[8], bt[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int g = (c0 + j) / gs;
+    mu[j] = a.mean_rstd[2 * g];
+    sc[j] = a.mean_rstd[2 * g + 1] * __ldg(a.gamma + c0 + j);
+    bt[j] = __ldg(a.beta + c0 + j);
+  }
+  const uint32_t n_rows = (uint32_t)a.N;
+  const uint32_t stride = gridDim.x * rows_per_blk;
+  const uint32_t hw = SPATIAL ? uint32_t(a.H) * a.W : 1u;
+  for (uint32_t r0 = blockIdx.x * rows_per_blk + row_in_blk; r0 < n_rows; r0 += 4 * stride) {
+    uint4 xin[4], zyv[4], zbv[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int64_t i = i0 + k * gstride;
-      if (i < total) xin[k] = __ldg(reinterpret_cast<const uint4*>(a.x) + i);
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-    const int64_t i = i0 + k * gstride;
-    if (i >= total) break;
-    const int64_t r = i / tpr;
-    const int c0 = int(i - r * tpr) * 8;
-    float f[8];
-    unpack8v(xin[k], f);
-    float gm[8], bt[8];
-    {
-      const float4 g0 = __ldg(reinterpret_cast<const float4*>(a.gamma + c0));
-      const float4 g1 = __ldg(reinterpret_cast<const float4*>(a.gamma + c0 + 4));
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.beta + c0));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(a.beta + c0 + 4));
-      gm[0] = g0.x; gm[1] = g0.y; gm[2] = g0.z; gm[3] = g0.w; gm[4] = g1.x; gm[5] = g1.y; gm[6] = g1.z; gm[7] = g1.w;
-      bt[0] = b0.x; bt[1] = b0.y; bt[2] = b0.z; bt[3] = b0.w; bt[4] = b1.x; bt[5] = b1.y; bt[6] = b1.z; bt[7] = b1.w;
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int g = (c0 + j) / gs;
-      const float m = a.mean_rstd[2 * g], rs = a.mean_rstd[2 * g + 1];
-      f[j] = (f[j] - m) * rs * gm[j] + bt[j];
-    }
-    if (a.zy != nullptr) {
-      const int hw = a.H * a.W;
-      const int t = int(r / hw);
-      const int rem = int(r - int64_t(t) * hw);
-      const int yy = rem / a.W, xx = rem - yy * a.W;
-      const int64_t zr = (int64_t(a.tmap[t]) * a.hz + (yy * a.hz) / a.H) * a.wz + (xx * a.wz) / a.W;
-      float zy[8], zb[8];
-      unpack8v(__ldg(reinterpret_cast<const uint4*>(a.zy + zr * a.zld + c0)), zy);
-      unpack8v(__ldg(reinterpret_cast<const uint4*>(a.zb + zr * a.zld + c0)), zb);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = bf16r(f[j]) * zy[j] + zb[j];   // norm_f is a bf16 tensor upstream
-    }
-    if (a.silu) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float v = bf16r(f[j]);                                   // activation input is the bf16 norm output
-        f[j] = v / (1.0f + __expf(-v));
+      const uint32_t r = r0 + k * stride;
+      if (r < n_rows) {
+        xin[k] = __ldg(reinterpret_cast<const uint4*>(a.x + int64_t(r) * a.C + c0));
+        if (SPATIAL) {
+          const uint32_t t = r / hw, rem = r - t * hw;
+          const uint32_t yy = rem / uint32_t(a.W), xx = rem - yy * uint32_t(a.W);
+          const int64_t zr = (int64_t(tmap[t]) * a.hz + (yy * uint32_t(a.hz)) / uint32_t(a.H)) * a.wz +
+                             (xx * uint32_t(a.wz)) / uint32_t(a.W);
+          zyv[k] = __ldg(reinterpret_cast<const uint4*>(a.zy + zr * a.zld + c0));
+          zbv[k] = __ldg(reinterpret_cast<const uint4*>(a.zb + zr * a.zld + c0));
+        }
       }
     }
-    *reinterpret_cast<uint4*>(a.y + r * a.C + c0) = pack8v(f);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t r = r0 + k * stride;
+      if (r >= n_rows) break;
+      float f[8];
+      unpack8v(xin[k], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j] - mu[j], sc[j], bt[j]);
+      if (SPATIAL) {
+        float zy[8], zb[8];
+        unpack8v(zyv[k], zy);
+        unpack8v(zbv[k], zb);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = fmaf(bf16r(f[j]), zy[j], zb[j]);   // norm_f is a bf16 tensor upstream
+      }
+      if (a.silu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float v = bf16r(f[j]);                                        // activation input is the bf16 norm output
+          f[j] = __fdividef(v, 1.0f + __expf(-v));
+        }
+      }
+      *reinterpret_cast<uint4*>(a.y + int64_t(r) * a.C + c0) = pack8v(f);
     }
   }
 }
@@ -190,8 +200,9 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyArgs a) {
 // out[t', y', x', :] = in[tmap[t'], y' / sy, x' / sx, :]      nearest up-sampling (F.interpolate) incl. the
 // "keep the first frame" temporal rule, which the host encodes in tmap.   Bytes: (1 + sy*sx*T'/T) * |in|.
 // ------------------------------------------------------------------------------------------------
+template <class MapT>
 __global__ void __launch_bounds__(256)
-upsample_nearest_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const int* __restrict__ tmap, int To,
+upsample_nearest_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const MapT tmap, int To,
                         int Ho, int Wo, int Hi, int Wi, int sy, int sx, int cvec) {
   const int64_t total = int64_t(To) * Ho * Wo * cvec;
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
@@ -205,9 +216,10 @@ upsample_nearest_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, c
 }
 
 // out[t'] = in[a[t']] if b[t'] < 0 else avg(in[a[t']], in[b[t']])   (F.avg_pool1d(k=2,s=2) keeping frame 0; bf16)
+template <class MapT>
 __global__ void __launch_bounds__(256)
-avgpool_time_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const int* __restrict__ ia,
-                    const int* __restrict__ ib, int To, int64_t frame_vecs) {
+avgpool_time_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, const MapT ia, const MapT ib, int To,
+                    int64_t frame_vecs) {
   const int64_t total = int64_t(To) * frame_vecs;
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
     const int t = int(i / frame_vecs);
@@ -299,6 +311,131 @@ static unsigned sgrid(int64_t n) {
   return (unsigned)(g > cap ? cap : (g < 1 ? 1 : g));
 }
 
+// crop of an NCTHW tensor (element strides sC, sT, sH; unit stride along W) -> channels-last [T, H, W, Cp], channels
+// >= C zeroed: the `x[:, s:e, i:i+th, j:j+tw]` slices of the tiled / frame-batched VAE without a .contiguous() copy.
+__global__ void __launch_bounds__(256)
+crop_ncthw_to_thwc_kernel(const __nv_bfloat16* __restrict__ in, int64_t sC, int64_t sT, int64_t sH,
+                          __nv_bfloat16* __restrict__ out, int C, int Cp, int T, int H, int W) {
+  const int64_t total = int64_t(T) * H * W * Cp;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int c = int(i % Cp);
+    int64_t p = i / Cp;
+    const int x = int(p % W); p /= W;
+    const int y = int(p % H);
+    const int t = int(p / H);
+    out[i] = c < C ? in[c * sC + t * sT + y * sH + x] : __float2bfloat16(0.f);
+  }
+}
+
+// dst[t, y0 + y, x0 + x, :] = src[t, y, x, :] for y < h, x < w (channels-last, 16-byte vectors): writes the kept part
+// of a blended VAE tile into the assembled output (torch.cat of `tile[:, :lim_h, :lim_w]` in diffusers).
+__global__ void __launch_bounds__(256)
+copy_region_kernel(const uint4* __restrict__ src, int Hs, int Ws, uint4* __restrict__ dst, int Hd, int Wd, int T, int h,
+                   int w, int cvec, int y0, int x0) {
+  const int64_t total = int64_t(T) * h * w * cvec;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int cv = int(i % cvec);
+    int64_t p = i / cvec;
+    const int x = int(p % w); p /= w;
+    const int y = int(p % h);
+    const int t = int(p / h);
+    dst[((int64_t(t) * Hd + y0 + y) * Wd + x0 + x) * cvec + cv] = __ldg(src + ((int64_t(t) * Hs + y) * Ws + x) * cvec + cv);
+  }
+}
+
+// ---- C++ entry points for the handle-level executor (vae_exec.cu): index maps by value, no device-side tables
+int gn_apply_imap(const void* x, void* y, int64_t N, int C, int G, const float* mean_rstd, const float* gamma,
+                  const float* beta, const void* zy, const void* zb, int zld, const IMap* tmap, int H, int W, int hz,
+                  int wz, int silu, cudaStream_t stream) {
+  AETHER_CHECK_ARG(x && y && mean_rstd && gamma && beta && N > 0 && C % 8 == 0 && C % G == 0);
+  AETHER_CHECK_ARG(256 % (C / 8) == 0 && N < (int64_t(1) << 31) && (C / G) % 4 == 0);
+  GnApplyArgs a{reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y), N, C, G, mean_rstd, gamma,
+                beta, reinterpret_cast<const __nv_bfloat16*>(zy), reinterpret_cast<const __nv_bfloat16*>(zb), H, W, hz, wz,
+                zld > 0 ? zld : C, silu};
+  const int rows_per_blk = 256 / (C / 8);
+  int64_t blocks = ceil_div(N, int64_t(rows_per_blk) * 4);
+  const int64_t cap = int64_t(num_sms()) * 8;
+  if (blocks > cap) blocks = cap;
+  if (zy != nullptr) {
+    AETHER_CHECK_ARG(zb && tmap);
+    gn_apply_kernel<true, IMap><<<(unsigned)blocks, 256, 0, stream>>>(a, *tmap);
+  } else {
+    gn_apply_kernel<false, const int*><<<(unsigned)blocks, 256, 0, stream>>>(a, nullptr);
+  }
+  AETHER_CUDA_OK(cudaGetLastError());
+  return AETHER_OK;
+}
+int upsample_nearest_imap(const void* in, void* out, const IMap& tmap, int To, int Ho, int Wo, int Hi, int Wi, int sy,
+                          int sx, int C, cudaStream_t stream) {
+  AETHER_CHECK_ARG(in && out && C % 8 == 0 && Ho == Hi * sy && Wo == Wi * sx && To <= IMap::kMax);
+  upsample_nearest_kernel<IMap><<<sgrid(int64_t(To) * Ho * Wo * (C / 8)), 256, 0, stream>>>(
+      reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), tmap, To, Ho, Wo, Hi, Wi, sy, sx, C / 8);
+  AETHER_CUDA_OK(cudaGetLastError());
+  return AETHER_OK;
+}
+int avgpool_time_imap(const void* in, void* out, const IMap& ia, const IMap& ib, int To, int64_t frame_elems,
+                      cudaStream_t stream) {
+  AETHER_CHECK_ARG(in && out && frame_elems % 8 == 0 && To <= IMap::kMax);
+  avgpool_time_kernel<IMap><<<sgrid(int64_t(To) * frame_elems / 8), 256, 0, stream>>>(
+      reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), ia, ib, To, frame_elems / 8);
+  AETHER_CUDA_OK(cudaGetLastError());
+  return AETHER_OK;
+}
+int crop_ncthw_to_thwc(const void* in, int64_t sC, int64_t sT, int64_t sH, void* out, int C, int Cp, int T, int H, int W,
+                       cudaStream_t stream) {
+  AETHER_CHECK_ARG(in && out && C <= Cp);
+  crop_ncthw_to_thwc_kernel<<<sgrid(int64_t(T) * H * W * Cp), 256, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(in), sC, sT, sH, reinterpret_cast<__nv_bfloat16*>(out), C, Cp, T, H, W);
+  AETHER_CUDA_OK(cudaGetLastError());
+  return AETHER_OK;
+}
+int copy_region_cl(const void* src, int Hs, int Ws, void* dst, int Hd, int Wd, int T, int h, int w, int C, int y0, int x0,
+                   cudaStream_t stream) {
+  AETHER_CHECK_ARG(src && dst && C % 8 == 0 && h <= Hs && w <= Ws && y0 + h <= Hd && x0 + w <= Wd);
+  copy_region_kernel<<<sgrid(int64_t(T) * h * w * (C / 8)), 256, 0, stream>>>(
+      reinterpret_cast<const uint4*>(src), Hs, Ws, reinterpret_cast<uint4*>(dst), Hd, Wd, T, h, w, C / 8, y0, x0);
+  AETHER_CUDA_OK(cudaGetLastError());
+  return AETHER_OK;
+}
+
+int64_t gn_workspace_floats(int C) { return int64_t(num_sms()) * 8 * (C / 4) * 2; }
+
+int gn_stats(const void* x, int64_t N, int C, int G, float eps, float* workspace, float* mean_rstd,
+             cudaStream_t stream) {
+  AETHER_CHECK_ARG(x && workspace && mean_rstd && N > 0 && C % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0 &&
+                   C % G == 0 && (C / G) % 4 == 0);
+  const int rows_per_blk = 256 / (C / 8);
+  int nblocks = (int)ceil_div(N, rows_per_blk);
+  const int cap = num_sms() * 8;       // 8 resident blocks of 256 threads per SM
+  if (nblocks > cap) nblocks = cap;
+  gn_partial_kernel<<<nblocks, 256, 256 * 4 * sizeof(float), stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), N, C,
+                                                                         workspace);
+  const int fin_threads = G * 32 < 1024 ? G * 32 : 1024;      // one warp per group
+  gn_finalize_kernel<<<1, fin_threads, 0, stream>>>(workspace, nblocks, C, G, double(N) * (C / G), eps, mean_rstd);
+  AETHER_CUDA_OK(cudaGetLastError());
+  return AETHER_OK;
+}
+
+int tile_blend(const void* a, void* b, int T, int Ha, int Wa, int Hb, int Wb, int C, int axis, int extent,
+               cudaStream_t stream) {
+  AETHER_CHECK_ARG(a && b && (axis == 1 || axis == 2) && extent > 0);
+  AETHER_CHECK_ARG(!(axis == 1 && (extent > Ha || extent > Hb || Wa != Wb)) &&
+                   !(axis == 2 && (extent > Wa || extent > Wb || Ha != Hb)));
+  const int64_t n = int64_t(T) * (axis == 1 ? extent : Hb) * (axis == 2 ? extent : Wb) * C;
+  tile_blend_kernel<<<sgrid(n), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(a),
+                                                  reinterpret_cast<__nv_bfloat16*>(b), T, Ha, Wa, Hb, Wb, C, axis, extent);
+  AETHER_CUDA_OK(cudaGetLastError());
+  return AETHER_OK;
+}
+
+int thwc_to_ncthw(const void* in, void* out, int C, int Cp, int64_t thw, cudaStream_t stream) {
+  AETHER_CHECK_ARG(in && out && C <= Cp);
+  thwc_to_ncthw_kernel<<<sgrid(thw * C), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(in),
+                                                           reinterpret_cast<__nv_bfloat16*>(out), C, Cp, thw);
+  AETHER_CUDA_OK(cudaGetLastError());
+  return AETHER_OK;
+}
+
 }  // namespace aether
 
 using namespace aether;
@@ -307,21 +444,11 @@ using namespace aether;
 #define CBF(p) reinterpret_cast<const __nv_bfloat16*>(p)
 extern "C" {
 
-int64_t aether_gn_workspace_floats(int32_t C) { return int64_t(num_sms()) * 8 * (C / 4) * 2; }
+int64_t aether_gn_workspace_floats(int32_t C) { return gn_workspace_floats(C); }
 
 int aether_gn_stats(const void* x, int64_t N, int32_t C, int32_t G, float eps, float* workspace, float* mean_rstd,
                     void* stream) {
-  if (!x || !workspace || !mean_rstd || N <= 0 || C % 8 != 0 || C > 2048 || 256 % (C / 8) != 0 || C % G != 0 ||
-      (C / G) % 4 != 0)
-    return AETHER_ERR_INVALID;
-  const int rows_per_blk = 256 / (C / 8);
-  int nblocks = (int)ceil_div(N, rows_per_blk);
-  const int cap = num_sms() * 8;       // 8 resident blocks of 256 threads per SM
-  if (nblocks > cap) nblocks = cap;
-  gn_partial_kernel<<<nblocks, 256, 256 * 4 * sizeof(float), ST(stream)>>>(CBF(x), N, C, workspace);
-  const int fin_threads = G * 32 < 1024 ? G * 32 : 1024;      // one warp per group
-  gn_finalize_kernel<<<1, fin_threads, 0, ST(stream)>>>(workspace, nblocks, C, G, double(N) * (C / G), eps, mean_rstd);
-  return cudaGetLastError() == cudaSuccess ? AETHER_OK : AETHER_ERR_CUDA;
+  return gn_stats(x, N, C, G, eps, workspace, mean_rstd, ST(stream));
 }
 
 int aether_gn_apply(const void* x, void* y, int64_t N, int32_t C, int32_t G, const float* mean_rstd,
@@ -330,15 +457,23 @@ int aether_gn_apply(const void* x, void* y, int64_t N, int32_t C, int32_t G, con
   if (!x || !y || !mean_rstd || !gamma || !beta || N <= 0 || C % 8 != 0 || C % G != 0) return AETHER_ERR_INVALID;
   if ((zy == nullptr) != (zb == nullptr) || (zy && (!tmap || H <= 0 || W <= 0 || hz <= 0 || wz <= 0)))
     return AETHER_ERR_INVALID;
-  GnApplyArgs a{CBF(x), BF(y), N, C, G, mean_rstd, gamma, beta, CBF(zy), CBF(zb), tmap, H, W, hz, wz, zld > 0 ? zld : C, silu};
-  gn_apply_kernel<<<sgrid(ceil_div(N * (C / 8), 4)), 256, 0, ST(stream)>>>(a);
+  if (256 % (C / 8) != 0 || N >= (int64_t(1) << 31) || (C / G) % 4 != 0) return AETHER_ERR_INVALID;
+  GnApplyArgs a{CBF(x), BF(y), N, C, G, mean_rstd, gamma, beta, CBF(zy), CBF(zb), H, W, hz, wz, zld > 0 ? zld : C, silu};
+  const int rows_per_blk = 256 / (C / 8);
+  int64_t blocks = ceil_div(N, int64_t(rows_per_blk) * 4);
+  const int64_t cap = int64_t(num_sms()) * 8;
+  if (blocks > cap) blocks = cap;
+  if (zy != nullptr)
+    gn_apply_kernel<true, const int*><<<(unsigned)blocks, 256, 0, ST(stream)>>>(a, tmap);
+  else
+    gn_apply_kernel<false, const int*><<<(unsigned)blocks, 256, 0, ST(stream)>>>(a, nullptr);
   return cudaGetLastError() == cudaSuccess ? AETHER_OK : AETHER_ERR_CUDA;
 }
 
 int aether_upsample_nearest(const void* in, void* out, const int32_t* tmap, int32_t To, int32_t Ho, int32_t Wo,
                             int32_t Hi, int32_t Wi, int32_t sy, int32_t sx, int32_t C, void* stream) {
   if (!in || !out || !tmap || C % 8 != 0 || Ho != Hi * sy || Wo != Wi * sx) return AETHER_ERR_INVALID;
-  upsample_nearest_kernel<<<sgrid(int64_t(To) * Ho * Wo * (C / 8)), 256, 0, ST(stream)>>>(
+  upsample_nearest_kernel<const int*><<<sgrid(int64_t(To) * Ho * Wo * (C / 8)), 256, 0, ST(stream)>>>(
       reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), tmap, To, Ho, Wo, Hi, Wi, sy, sx, C / 8);
   return cudaGetLastError() == cudaSuccess ? AETHER_OK : AETHER_ERR_CUDA;
 }
@@ -346,7 +481,7 @@ int aether_upsample_nearest(const void* in, void* out, const int32_t* tmap, int3
 int aether_avgpool_time(const void* in, void* out, const int32_t* ia, const int32_t* ib, int32_t To,
                         int64_t frame_elems, void* stream) {
   if (!in || !out || !ia || !ib || frame_elems % 8 != 0) return AETHER_ERR_INVALID;
-  avgpool_time_kernel<<<sgrid(int64_t(To) * frame_elems / 8), 256, 0, ST(stream)>>>(
+  avgpool_time_kernel<const int*><<<sgrid(int64_t(To) * frame_elems / 8), 256, 0, ST(stream)>>>(
       reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), ia, ib, To, frame_elems / 8);
   return cudaGetLastError() == cudaSuccess ? AETHER_OK : AETHER_ERR_CUDA;
 }
@@ -357,9 +492,7 @@ int aether_ncthw_to_thwc(const void* in, void* out, int32_t C, int32_t Cp, int64
   return cudaGetLastError() == cudaSuccess ? AETHER_OK : AETHER_ERR_CUDA;
 }
 int aether_thwc_to_ncthw(const void* in, void* out, int32_t C, int32_t Cp, int64_t thw, void* stream) {
-  if (!in || !out || C > Cp) return AETHER_ERR_INVALID;
-  thwc_to_ncthw_kernel<<<sgrid(thw * C), 256, 0, ST(stream)>>>(CBF(in), BF(out), C, Cp, thw);
-  return cudaGetLastError() == cudaSuccess ? AETHER_OK : AETHER_ERR_CUDA;
+  return thwc_to_ncthw(in, out, C, Cp, thw, ST(stream));
 }
 int aether_posterior_sample(const void* moments, int32_t Cp, int32_t L, const void* noise, void* z, int64_t P,
                             void* stream) {
@@ -370,11 +503,6 @@ int aether_posterior_sample(const void* moments, int32_t Cp, int32_t L, const vo
 }
 int aether_tile_blend(const void* a, void* b, int32_t T, int32_t Ha, int32_t Wa, int32_t Hb, int32_t Wb, int32_t C,
                       int32_t axis, int32_t extent, void* stream) {
-  if (!a || !b || (axis != 1 && axis != 2) || extent <= 0) return AETHER_ERR_INVALID;
-  if ((axis == 1 && (extent > Ha || extent > Hb || Wa != Wb)) || (axis == 2 && (extent > Wa || extent > Wb || Ha != Hb)))
-    return AETHER_ERR_INVALID;
-  const int64_t n = int64_t(T) * (axis == 1 ? extent : Hb) * (axis == 2 ? extent : Wb) * C;
-  tile_blend_kernel<<<sgrid(n), 256, 0, ST(stream)>>>(CBF(a), BF(b), T, Ha, Wa, Hb, Wb, C, axis, extent);
-  return cudaGetLastError() == cudaSuccess ? AETHER_OK : AETHER_ERR_CUDA;
+  return tile_blend(a, b, T, Ha, Wa, Hb, Wb, C, axis, extent, ST(stream));
 }
 }

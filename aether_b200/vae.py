@@ -191,6 +191,14 @@ class AetherVAE(nn.Module):
         self._packed: Optional[Dict[str, dict]] = None
         self._imaps: Dict[tuple, torch.Tensor] = {}
         self._gn_ws = None
+        self._handle = None
+        self._handle_tiling = False
+        self._ws = None
+        # True: orchestrate every kernel from Python through the per-kernel C entry points (the path of round 1, kept so
+        # that each kernel stays individually testable and as the cross-check of the native schedule); False: one
+        # aether_vae_encode / aether_vae_decode call per batch item.  AETHER_VAE_PER_OP=1 selects it globally.
+        import os
+        self.per_op = os.environ.get("AETHER_VAE_PER_OP", "0")[:1] == "1"
 
     # ------------------------------------------------------------------ surface
     @property
@@ -212,6 +220,8 @@ class AetherVAE(nn.Module):
         self._packed = None
         self._imaps = {}
         self._gn_ws = None
+        self._destroy_handle()
+        self._ws = None
         return r
 
     @torch.no_grad()
@@ -298,7 +308,105 @@ class AetherVAE(nn.Module):
         spatial("decoder.norm_out", d.norm_out)
         conv("decoder.conv_out", d.conv_out.conv)
         self._packed = P
+        self._create_handle()
         return self
+
+    # ------------------------------------------------------------------ native handle (whole schedule in one C call)
+    def _tiling_ints(self):
+        """The int(...) arithmetic of diffusers tiled_encode / tiled_decode, evaluated once here and handed to the C side
+        (stride between tiles, blend extent, kept extent)."""
+        oh, ow = self.tile_overlap_factor_height, self.tile_overlap_factor_width
+        e_bl_h, e_bl_w = int(self.tile_latent_min_height * oh), int(self.tile_latent_min_width * ow)
+        d_bl_h, d_bl_w = int(self.tile_sample_min_height * oh), int(self.tile_sample_min_width * ow)
+        return dict(
+            enc_overlap_h=int(self.tile_sample_min_height * (1 - oh)), enc_overlap_w=int(self.tile_sample_min_width * (1 - ow)),
+            enc_blend_h=e_bl_h, enc_blend_w=e_bl_w, enc_limit_h=self.tile_latent_min_height - e_bl_h,
+            enc_limit_w=self.tile_latent_min_width - e_bl_w,
+            dec_overlap_h=int(self.tile_latent_min_height * (1 - oh)), dec_overlap_w=int(self.tile_latent_min_width * (1 - ow)),
+            dec_blend_h=d_bl_h, dec_blend_w=d_bl_w, dec_limit_h=self.tile_sample_min_height - d_bl_h,
+            dec_limit_w=self.tile_sample_min_width - d_bl_w)
+
+    def _create_handle(self):
+        import ctypes as C
+        lib = _lib.require_device()
+        self._destroy_handle()
+        c = self.config
+        cfg = _lib.VaeConfig()
+        for k, v in dict(
+                in_channels=c.in_channels, out_channels=c.out_channels, latent_channels=c.latent_channels,
+                num_blocks=len(c.block_out_channels), layers_per_block=c.layers_per_block,
+                norm_num_groups=c.norm_num_groups, norm_eps=float(c.norm_eps),
+                temporal_compression_ratio=c.temporal_compression_ratio, use_tiling=int(self.use_tiling),
+                num_latent_frames_batch_size=self.num_latent_frames_batch_size,
+                num_sample_frames_batch_size=self.num_sample_frames_batch_size,
+                tile_sample_min_height=self.tile_sample_min_height, tile_sample_min_width=self.tile_sample_min_width,
+                tile_latent_min_height=self.tile_latent_min_height, tile_latent_min_width=self.tile_latent_min_width,
+                **self._tiling_ints()).items():
+            setattr(cfg, k, v)
+        items = sorted(self._packed.items())
+        arr = (_lib.VaeParam * len(items))()
+        keep = []
+        for i, (name, p) in enumerate(items):
+            nb = name.encode()
+            keep.append(nb)
+            arr[i].name = nb
+            if "k" in p:
+                arr[i].kind, arr[i].data, arr[i].bias = 0, p["w"].data_ptr(), p["b"].data_ptr()
+                arr[i].kt, arr[i].kh, arr[i].kw = p["k"]
+                arr[i].cin, arr[i].cout = p["cin"], p["cout"]
+            elif "g" in p:
+                arr[i].kind, arr[i].data, arr[i].bias = 1, p["g"].data_ptr(), p["b"].data_ptr()
+            else:
+                arr[i].kind, arr[i].data, arr[i].bias = 2, p["w"].data_ptr(), p["b"].data_ptr()
+        h = C.c_void_p()
+        check(lib.aether_vae_create(C.byref(cfg), arr, len(items), C.byref(h)), "vae_create")
+        self._handle, self._handle_tiling = h, bool(self.use_tiling)
+        self._ws = None
+
+    def _destroy_handle(self):
+        if getattr(self, "_handle", None) is not None:
+            _lib.load().aether_vae_destroy(self._handle)
+        self._handle = None
+
+    def __del__(self):
+        try:
+            self._destroy_handle()
+        except Exception:
+            pass
+
+    def _native(self, op: int, x: torch.Tensor):
+        """x: bf16 [C, T, H, W] (any T/H strides, unit W stride) -> channels-last moments (op 0) or NCTHW frames (op 1)."""
+        import ctypes as C
+        lib = _lib.load()
+        if self._handle is None or self._handle_tiling != bool(self.use_tiling):
+            self._create_handle()                       # enable_tiling() after pack(): the handle carries the flag
+        if x.stride(3) != 1:
+            x = x.contiguous()
+        Cc, T, H, W = x.shape
+        dims = (C.c_int32 * 4)()
+        check(lib.aether_vae_output_shape(self._handle, op, T, H, W, dims), "vae_output_shape")
+        need = lib.aether_vae_workspace_bytes(self._handle, op, T, H, W)
+        if need < 0:
+            raise RuntimeError("aether_vae_workspace_bytes failed")
+        if self._ws is None or self._ws.numel() < need or self._ws.device != x.device:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=x.device)
+        To, Ho, Wo, Co = (int(v) for v in dims)
+        if op == 0:
+            out = torch.empty(To, Ho, Wo, Co, dtype=BF16, device=x.device)
+            fn, what = lib.aether_vae_encode, "vae_encode"
+        else:
+            out = torch.empty(self.config.out_channels, To, Ho, Wo, dtype=BF16, device=x.device)
+            fn, what = lib.aether_vae_decode, "vae_decode"
+        check(fn(self._handle, ptr(x), x.stride(0), x.stride(1), x.stride(2), T, H, W, ptr(out), ptr(self._ws),
+                 self._ws.numel(), current_stream()), what)
+        return out
+
+    def launches(self, op: int, T: int, H: int, W: int) -> int:
+        """Kernel launches + device copies one native encode (op 0, pixels) / decode (op 1, latent size) enqueues."""
+        self.pack()
+        if self._handle_tiling != bool(self.use_tiling):
+            self._create_handle()
+        return int(_lib.load().aether_vae_launch_count(self._handle, op, T, H, W))
 
     # ------------------------------------------------------------------ kernel wrappers (channels-last tensors)
     def _imap(self, vals) -> torch.Tensor:
@@ -531,7 +639,8 @@ class AetherVAE(nn.Module):
         if not x.is_cuda:
             raise RuntimeError("AetherVAE.encode: input must be a CUDA tensor (no CPU path)")
         x = x.to(BF16)
-        posts = [_Posterior(self._encode_one(xi), self.config.latent_channels) for xi in x]
+        one = self._encode_one if self.per_op else (lambda xi: self._native(0, xi))
+        posts = [_Posterior(one(xi), self.config.latent_channels) for xi in x]
         post = posts[0] if len(posts) == 1 else _CatPosterior(posts)
         return SimpleNamespace(latent_dist=post)
 
@@ -543,6 +652,8 @@ class AetherVAE(nn.Module):
         if not z.is_cuda:
             raise RuntimeError("AetherVAE.decode: input must be a CUDA tensor (no CPU path)")
         z = z.to(BF16)
+        if not self.per_op:
+            return SimpleNamespace(sample=torch.stack([self._native(1, zi) for zi in z], dim=0))
         outs = []
         for zi in z:
             y = self._decode_one(zi)                                   # [T, H, W, 8]

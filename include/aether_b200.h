@@ -225,6 +225,55 @@ int aether_posterior_sample(const void* moments, int32_t Cp, int32_t L, const vo
 int aether_tile_blend(const void* a, void* b, int32_t T, int32_t Ha, int32_t Wa, int32_t Hb, int32_t Wb, int32_t C,
                       int32_t axis, int32_t extent, void* stream);
 
+/* ---------------------------------------------------------------- 3-D causal VAE, handle level
+ * aether_vae_encode / aether_vae_decode run the whole AutoencoderKLCogVideoX.encode / .decode schedule of ONE batch item
+ * (3 x 3 spatial tiling + tile blends, frame batching with conv caches, every resnet / norm / resampling stage) as one
+ * call that only enqueues kernels on `stream`: the `vae_encode_tile` / `vae_decode_tile` entry points of SURVEY.md 8(b).
+ * Device work behind vae.encode(x).latent_dist (pipeline :557-620) and vae.decode(z).sample (:931, :936). */
+typedef struct AetherVaeConfig {
+  int32_t in_channels, out_channels, latent_channels;
+  int32_t num_blocks;                /* len(block_out_channels); channel counts come with the parameters */
+  int32_t layers_per_block, norm_num_groups;
+  float norm_eps;
+  int32_t temporal_compression_ratio;
+  int32_t use_tiling;
+  int32_t num_latent_frames_batch_size, num_sample_frames_batch_size;   /* diffusers: 2 and 8 */
+  int32_t tile_sample_min_height, tile_sample_min_width, tile_latent_min_height, tile_latent_min_width;
+  /* tiling arithmetic of diffusers tiled_encode / tiled_decode, evaluated by the caller (int(...) of float expressions):
+   * stride between tiles, blend extent, kept extent -- in input pixels / latent pixels as appropriate */
+  int32_t enc_overlap_h, enc_overlap_w, enc_blend_h, enc_blend_w, enc_limit_h, enc_limit_w;
+  int32_t dec_overlap_h, dec_overlap_w, dec_blend_h, dec_blend_w, dec_limit_h, dec_limit_w;
+} AetherVaeConfig;
+
+/* One packed parameter, addressed by its diffusers state-dict prefix (e.g. "decoder.up_blocks.0.resnets.1.conv1"):
+ *   kind 0  convolution: data = bf16 [cout, kt*kh*kw*ceil64(cin)] (aether_conv3d_bf16 layout), bias fp32 [cout]
+ *   kind 1  GroupNorm affine ("...norm1" for the encoder, "...norm1.norm_layer" for SpatialNorm3D): data = gamma fp32,
+ *           bias = beta fp32
+ *   kind 2  SpatialNorm3D conv_y | conv_b fused ("...norm1.conv_yb"): data = bf16 [2C, latent_channels], bias fp32 [2C] */
+typedef struct AetherVaeParam {
+  const char* name;
+  int32_t kind;
+  const void* data;
+  const float* bias;
+  int32_t kt, kh, kw, cin, cout;     /* kind 0 only */
+} AetherVaeParam;
+
+typedef struct AetherVae AetherVae;
+int aether_vae_create(const AetherVaeConfig* cfg, const AetherVaeParam* params, int32_t n_params, AetherVae** out);
+void aether_vae_destroy(AetherVae* h);
+/* op: 0 = encode of x[C, T, H, W] pixels, 1 = decode of z[L, T, H, W] latents.  Scratch bytes / number of kernel launches
+ * and copies / result dims {T', H', W', C'} (channels-last moments for op 0, decoded frames for op 1) of one call. */
+int64_t aether_vae_workspace_bytes(const AetherVae* h, int32_t op, int32_t T, int32_t H, int32_t W);
+int64_t aether_vae_launch_count(const AetherVae* h, int32_t op, int32_t T, int32_t H, int32_t W);
+int aether_vae_output_shape(const AetherVae* h, int32_t op, int32_t T, int32_t H, int32_t W, int32_t* dims4);
+/* x: bf16 [in_channels, T, H, W] with element strides (stride_c, stride_t, stride_h, 1) -> moments: channels-last bf16
+ * [T', H/8, W/8, ceil8(2 * latent_channels)] = (mean | logvar) of the posterior (input of aether_posterior_sample). */
+int aether_vae_encode(const AetherVae* h, const void* x, int64_t stride_c, int64_t stride_t, int64_t stride_h, int32_t T,
+                      int32_t H, int32_t W, void* moments, void* workspace, int64_t workspace_bytes, void* stream);
+/* z: bf16 [latent_channels, T, H, W] (strides as above) -> sample: contiguous bf16 [out_channels, T', 8H, 8W]. */
+int aether_vae_decode(const AetherVae* h, const void* z, int64_t stride_c, int64_t stride_t, int64_t stride_h, int32_t T,
+                      int32_t H, int32_t W, void* sample, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------- scheduler step (K8) */
 
 typedef struct AetherDpmCoeffs {

@@ -153,3 +153,40 @@ def test_vae_slicing_batch2():
     got = vae.decode(z.to(DEV)).sample
     rel, mx = _rel(got, ref)
     assert got.shape == ref.shape and rel < 2.5e-2, (rel, mx)
+
+
+# ---------------------------------------------------------------------------------------- native schedule (C ABI handle)
+@pytest.mark.parametrize("tiling", [False, True])
+def test_native_schedule_equals_per_op_schedule(tiling):
+    """aether_vae_encode / aether_vae_decode (whole schedule in one C call, arena workspace) launch the same kernels on
+    the same operands in the same order as the per-op Python orchestration: results must be bit-identical."""
+    cfg, oracle, vae = _build_vae(seed=4)
+    if tiling:
+        vae.enable_tiling()
+    g = torch.Generator().manual_seed(9)
+    x = (torch.rand(1, 3, 17, 96, 160, generator=g) * 2 - 1).to(BF16).to(DEV)
+    z = torch.randn(1, 16, 5, 12, 20, generator=g).to(BF16).to(DEV)
+    vae.per_op = True
+    m_ref = vae.encode(x).latent_dist.mode().clone()
+    d_ref = vae.decode(z).sample.clone()
+    vae.per_op = False
+    m = vae.encode(x).latent_dist.mode()
+    d = vae.decode(z).sample
+    assert torch.equal(m, m_ref) and torch.equal(d, d_ref)
+    # strided views (the pipeline hands over permuted tensors) go through the crop kernel unchanged
+    zt = z.permute(0, 2, 1, 3, 4).contiguous().permute(0, 2, 1, 3, 4)
+    assert not zt.is_contiguous() and torch.equal(vae.decode(zt).sample, d_ref)
+    assert vae.launches(1, 5, 12, 20) > 100 and vae.launches(0, 17, 96, 160) > 100
+
+
+def test_native_schedule_workspace_too_small_is_reported():
+    from aether_b200 import _lib
+    from aether_b200._lib import current_stream, ptr
+    cfg, oracle, vae = _build_vae(seed=4)
+    vae.pack()
+    z = torch.randn(16, 3, 12, 20).to(BF16).to(DEV)
+    out = torch.empty(3, 9, 96, 160, dtype=BF16, device=DEV)
+    ws = torch.empty(4096, dtype=torch.uint8, device=DEV)
+    rc = _lib.load().aether_vae_decode(vae._handle, ptr(z), z.stride(0), z.stride(1), z.stride(2), 3, 12, 20, ptr(out),
+                                       ptr(ws), ws.numel(), current_stream())
+    assert rc == 3          # AETHER_ERR_WORKSPACE, nothing launched past the failing allocation
