@@ -52,10 +52,10 @@ struct Params {
   float scale_log2;         // dh^-0.5 * log2(e)
 };
 
-template <int MODE>   // 0: bf16 P/V   1: fp16 P/V, MUFU exp   2: fp16 P/V, 40% of the exponentials on the FMA pipe
+template <int MODE>   // 0: bf16 P/V   (1: fp16 P/V, MUFU exp -- not built)   2: fp16 P/V, 40% of the exponentials on the FMA pipe
 __global__ void __launch_bounds__(THREADS, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Params p) {
-  constexpr bool F16PV = (MODE == 1 || MODE == 2);   // MODE 3: bf16 P/V with the chunked two-pass softmax
+  constexpr bool F16PV = (MODE == 1 || MODE == 2);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_q = smem;                               // 2 tiles
@@ -249,75 +249,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Params p) {
     float l = 0.f;                                 // row sum (F16PV: kept in TMEM by the Ones MMA instead)
     uint32_t sph = 0;
 
-    if (MODE == 3) {
-      // ---- chunked two-pass variant (bf16 P/V): pass A reads S in 32-column chunks for the row max only, pass B
-      // re-reads each chunk, exponentiates, packs and stores it.  Only ~48 registers are live per chunk, so the
-      // scheduler can overlap the next chunk's TMEM load with the current chunk's MUFU/FMA work.
-      for (int j = 0; j < n_kv; ++j) {
-        mbar_wait(&s_full[t], sph);
-        sph ^= 1;
-        tc_fence_after();
-        const int kv_valid = p.S - j * BKV;
-        float m_tile = -INFINITY;
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(s_addr + ch * 32, v);
-          tc_wait_ld();
-          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            const float sv = (ch * 32 + c < kv_valid) ? __uint_as_float(v[c]) : -INFINITY;
-            m4[c & 3] = fmaxf(m4[c & 3], sv);
-          }
-          m_tile = fmaxf(m_tile, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
-        }
-        const float m_new = fmaxf(m_used, m_tile);
-        const bool need = (m_new - m_used) > rescale_thresh;
-        if (__any_sync(0xffffffffu, need)) {
-          const float alpha = fast_exp2((m_used - m_new) * sl2);
-          l *= alpha;
-          m_used = m_new;
-          if (j > 0) {
-            uint32_t o0[32], o1[32];
-            tmem_ld_32x32b_x32(o_addr, o0);
-            tmem_ld_32x32b_x32(o_addr + 32, o1);
-            tc_wait_ld();
-#pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              o0[c] = __float_as_uint(__uint_as_float(o0[c]) * alpha);
-              o1[c] = __float_as_uint(__uint_as_float(o1[c]) * alpha);
-            }
-            tmem_st_32x32b_x32(o_addr, o0);
-            tmem_st_32x32b_x32(o_addr + 32, o1);
-          }
-        }
-        const float neg_m = -m_used * sl2;
-        float sum4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(s_addr + ch * 32, v);
-          tc_wait_ld();
-          uint32_t pk[16];
-#pragma unroll
-          for (int c = 0; c < 32; c += 2) {
-            float p0 = fast_exp2(fmaf(__uint_as_float(v[c]), sl2, neg_m));
-            float p1 = fast_exp2(fmaf(__uint_as_float(v[c + 1]), sl2, neg_m));
-            if (ch * 32 + c >= kv_valid) p0 = 0.f;
-            if (ch * 32 + c + 1 >= kv_valid) p1 = 0.f;
-            sum4[(c >> 1) & 3] += p0 + p1;
-            pk[c >> 1] = pack_bf16x2(p0, p1);
-          }
-          // P chunk ch occupies packed columns [16 ch, 16 ch + 16) of the aliased S region: already consumed
-          tmem_st_32x32b_x16(s_addr + ch * 16, pk);
-        }
-        l += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
-        tc_wait_st();
-        tc_fence_before();
-        mbar_arrive(&p_full[t]);
-      }
-    } else
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(&s_full[t], sph);
       sph ^= 1;
@@ -465,19 +396,11 @@ static int launch(const CUtensorMap& tm, const Params& p, dim3 grid, cudaStream_
 
 }  // namespace attn
 
-int attention_v2_launch(const CUtensorMap& tm, int B, int S, int H, void* out, float scale_log2, cudaStream_t stream);
-int attention_v3_launch(const CUtensorMap& tm, int B, int S, int H, void* out, float scale_log2, int pipelined,
-                        cudaStream_t stream);
-int attention_v4_launch(const CUtensorMap& tm, int B, int S, int H, void* out, float scale_log2, cudaStream_t stream);
-int attention_v3_launch_blocks(const CUtensorMap& tm, int B, int S, int H, void* out, float scale_log2, int variant,
-                               int q_blocks, cudaStream_t stream);
-int attention_v4_launch_rows(const CUtensorMap& tm, int B, int S, int H, void* out, float scale_log2, int q_row0,
-                             cudaStream_t stream);
-int attention_v5_launch(const void* qkv, int B, int S, int H, void* out, float scale_log2, cudaStream_t stream);
-int attention_v6_launch(const void* qkv, int B, int S, int H, void* out, float scale_log2, cudaStream_t stream);
+int attention_v3_launch(const CUtensorMap& tm, int B, int S, int H, void* out, float scale_log2, cudaStream_t stream);
 
-// v_fp16 != 0: the V third of qkv holds fp16 values (GEMM f16_from_col) and an fp16-P mode runs:
-//   1 = every exponential on the MUFU, 2 = 40 % of them as an FMA-pipe polynomial (the product default).
+// `v_fp16` is the variant id: 5 = decoupled S / P TMEM buffers (product default, attention_v3_tcgen05.cu), 0 = baseline
+// (P aliases S), 2 = fp16 P/V (the V third of qkv then holds fp16 values, GEMM f16_from_col) with 40 % of the exponentials
+// as an FMA-pipe polynomial.
 int attention_bf16(const void* qkv, void* out, int B, int S, int H, float softmax_scale, int v_fp16,
                    cudaStream_t stream) {
   AETHER_CHECK_ARG(B > 0 && S > 0 && H > 0);
@@ -494,52 +417,12 @@ int attention_bf16(const void* qkv, void* out, int B, int S, int H, float softma
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
   dim3 grid((unsigned)ceil_div(S, 2 * attn::BQ), (unsigned)H, (unsigned)B);
   switch (v_fp16) {
-    case 0: return attn::launch<0>(tm, p, grid, stream);
-    case 1: return attn::launch<1>(tm, p, grid, stream);
-    case 2: return attn::launch<2>(tm, p, grid, stream);
-    case 4: return attention_v2_launch(tm, B, S, H, out, p.scale_log2, stream);   // 16 softmax warps (bf16 V)
-    case 5: return attention_v3_launch(tm, B, S, H, out, p.scale_log2, 0, stream);   // decoupled S / P buffers
-    case 6: return attention_v3_launch(tm, B, S, H, out, p.scale_log2, 1, stream);   // + per-warp pipelined softmax
-    case 7: return attention_v4_launch(tm, B, S, H, out, p.scale_log2, stream);      // 1 tile / CTA, 2 CTAs / SM
-    case 9: return attention_v3_launch(tm, B, S, H, out, p.scale_log2, 2, stream);   // mode 5 + 25 % polynomial exp2
-    case 10: return attention_v3_launch(tm, B, S, H, out, p.scale_log2, 3, stream);  // 12.5 %
-    case 11: return attention_v3_launch(tm, B, S, H, out, p.scale_log2, 4, stream);  // 37.5 %
-    case 14: {
-      // Split schedule: the complete 256-row query blocks on the mode-5 kernel, the ragged rest (S % 256 rows) as
-      // 128-row CTAs of the mode-7 kernel on a side stream.  The block scheduler drains the main grid first, so the
-      // tail CTAs land on the SMs the last, partially filled wave leaves idle (S = 15076, 48 heads: 2832 CTAs = 19.1
-      // waves become 2784 = 18.8 waves plus 96 half-size CTAs that run alongside the last wave).
-      const int full = S / (2 * attn::BQ);
-      if (full == 0 || S == full * 2 * attn::BQ) return attention_v3_launch(tm, B, S, H, out, p.scale_log2, 0, stream);
-      struct Side {
-        cudaStream_t s = nullptr;
-        cudaEvent_t fork = nullptr, join = nullptr;
-        bool ok = false;
-        Side() {
-          ok = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) == cudaSuccess &&
-               cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) == cudaSuccess &&
-               cudaEventCreateWithFlags(&join, cudaEventDisableTiming) == cudaSuccess;
-        }
-      };
-      static Side side;
-      if (!side.ok) return AETHER_ERR_CUDA;
-      AETHER_CUDA_OK(cudaEventRecord(side.fork, stream));
-      AETHER_CUDA_OK(cudaStreamWaitEvent(side.s, side.fork, 0));
-      rc = attention_v3_launch_blocks(tm, B, S, H, out, p.scale_log2, 0, full, stream);
-      if (rc) return rc;
-      rc = attention_v4_launch_rows(tm, B, S, H, out, p.scale_log2, full * 2 * attn::BQ, side.s);
-      if (rc) return rc;
-      AETHER_CUDA_OK(cudaEventRecord(side.join, side.s));
-      AETHER_CUDA_OK(cudaStreamWaitEvent(stream, side.join, 0));
-      return AETHER_OK;
-    }
-    case 13: return attention_v3_launch(tm, B, S, H, out, p.scale_log2, 5, stream);  // mode 5, consumers interleaved
-    case 12: return attention_v6_launch(qkv, B, S, H, out, p.scale_log2, stream);    // 3 query tiles, 12 softmax warps
-    case 8: return attention_v5_launch(qkv, B, S, H, out, p.scale_log2, stream);     // 64-key tiles, S load in flight
-    case 3: return attn::launch<3>(tm, p, grid, stream);    // bf16 V, chunked two-pass softmax
+    case 0: return attn::launch<0>(tm, p, grid, stream);                             // baseline: P aliases S
+    case 2: return attn::launch<2>(tm, p, grid, stream);                             // fp16 P/V + 40 % polynomial exp2
+    case 5: return attention_v3_launch(tm, B, S, H, out, p.scale_log2, stream);      // decoupled S / P buffers (default)
     default: break;
   }
-  AETHER_CHECK_ARG(!"unknown attention variant id (v_fp16 must be 0..14)");
+  AETHER_CHECK_ARG(!"unknown attention variant id (v_fp16 must be 0, 2 or 5)");
   return AETHER_ERR_INVALID;
 }
 

@@ -31,19 +31,9 @@ struct Params {
   float scale_log2;
 };
 
-// PIPE = false (mode 5): bulk S load, true row max, then exp.
-// PIPE = true  (mode 6): every softmax warp software-pipelines its own tile -- tcgen05.ld of 32-column chunk c+1 is in
-//   flight while chunk c goes through FFMA / MUFU / pack / tcgen05.st -- so both warps of a scheduler keep feeding
-//   the MUFU instead of one idling in a 1024-clk bulk load.  That requires the exponent offset BEFORE the tile has
-//   been seen: the running maximum of the previous tiles is used (the lazy-rescale invariant already tolerates an
-//   offset that is too small: P, l and O simply carry a common factor 2^excess in fp32/bf16), the true tile maximum
-//   is tracked on the side and applied to l immediately and to O at the start of the next tile (after PV_t(j) has
-//   retired).  If a tile ever exceeds the offset by more than 2^90 the tile is recomputed with its true maximum
-//   (S is still in TMEM), so no input can overflow.  The first tile establishes the offset with a max-only pass.
-// POLY_MASK (modes 9-11): bit (i & 7) set => the i-th PAIR of exponentials of a row is evaluated by the FMA-pipe
-// polynomial exp2_poly_f32x2 instead of two MUFU.EX2 (ncu after the uniform-issue fix: MUFU 77 % busy, MIO-throttle
-// stalls, FMA pipe 20 %, issue slots 46 %: the MUFU is the binding pipe, so a fraction of its work moves over).
-template <bool PIPE, int POLY_MASK>
+// Round-1 variants of this kernel (per-warp pipelined softmax, 12.5-37.5 % of the exponentials on the FMA pipe,
+// interleaved consumers, a split schedule for the ragged rows) measured equal or slower and live on, unbuilt, under
+// tools/experiments/attention/ together with the 16-softmax-warp, 1-tile-per-CTA, 64-key-tile and 3-query-tile kernels.
 __global__ void __launch_bounds__(THREADS, 1)
 attention_v3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -251,113 +241,6 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Params p
     const float rescale_thresh = 8.0f / sl2;
     float m_used = -INFINITY, l = 0.f;
 
-    if (PIPE) {
-      float o_alpha = 1.f;                          // factor still owed to O_t (applied once PV_t(j-1) has retired)
-      bool owe = false;                             // warp-uniform: some lane owes a factor
-      auto scale_O = [&](float alpha) {
-        uint32_t o0[32], o1[32];
-        tmem_ld_32x32b_x32(o_addr, o0);
-        tmem_ld_32x32b_x32(o_addr + 32, o1);
-        tc_wait_ld();
-#pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          o0[c] = __float_as_uint(__uint_as_float(o0[c]) * alpha);
-          o1[c] = __float_as_uint(__uint_as_float(o1[c]) * alpha);
-        }
-        tmem_st_32x32b_x32(o_addr, o0);
-        tmem_st_32x32b_x32(o_addr + 32, o1);
-      };
-      for (int j = 0; j < n_kv; ++j) {
-        mbar_wait(&s_full[t], j & 1);
-        tc_fence_after();
-        const int kv_valid = p.S - j * BKV;
-        const bool ragged = kv_valid < BKV;
-        if (j == 0) {                               // max-only pass: establishes the offset of the first tile
-          float m0 = -INFINITY;
-#pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
-            uint32_t v[32];
-            tmem_ld_32x32b_x32(s_addr + ch * 32, v);
-            tc_wait_ld();
-#pragma unroll
-            for (int c = 0; c < 32; ++c)
-              if (!ragged || ch * 32 + c < kv_valid) m0 = fmaxf(m0, __uint_as_float(v[c]));
-          }
-          m_used = m0;
-        }
-        const float l_prev = l;
-        bool p_writable = (j == 0);                 // P_t is free once PV_t(j-1) has retired
-#pragma unroll 1
-        for (int attempt = 0; attempt < 2; ++attempt) {
-          const float neg_m = -m_used * sl2;
-          float mrun[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-          float sum[4] = {0.f, 0.f, 0.f, 0.f};
-          uint32_t buf[2][32];
-          tmem_ld_32x32b_x32(s_addr, buf[0]);
-          tc_wait_ld();
-#pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
-            if (ch < 3) tmem_ld_32x32b_x32(s_addr + (ch + 1) * 32, buf[(ch + 1) & 1]);   // in flight during the math
-            uint32_t(&v)[32] = buf[ch & 1];
-            if (ragged) {                           // last key tile only: TMA zero-filled keys must not contribute
-#pragma unroll
-              for (int c = 0; c < 32; ++c)
-                if (ch * 32 + c >= kv_valid) v[c] = 0xFF800000u;
-            }
-            uint32_t pk[16];
-#pragma unroll
-            for (int c = 0; c < 32; c += 2) {
-              const float s0 = __uint_as_float(v[c]), s1 = __uint_as_float(v[c + 1]);
-              mrun[(c >> 1) & 3] = fmaxf(mrun[(c >> 1) & 3], fmaxf(s0, s1));
-              const float p0 = fast_exp2(fmaf(s0, sl2, neg_m));
-              const float p1 = fast_exp2(fmaf(s1, sl2, neg_m));
-              sum[(c >> 1) & 3] += p0 + p1;
-              pk[c >> 1] = pack_bf16x2(p0, p1);
-            }
-            if (ch == 0 && !p_writable) {           // first P store of the tile: PV_t(j-1) must have retired
-              mbar_wait(&p_free[t], (j - 1) & 1);
-              tc_fence_after();
-              p_writable = true;
-              if (owe) {                            // warp-uniform flag (set from a vote)
-                scale_O(o_alpha);
-                o_alpha = 1.f;
-                owe = false;
-              }
-            }
-            tmem_st_32x32b_x16(p_addr + ch * 16, pk);
-            if (ch < 3) tc_wait_ld();
-          }
-          const float m_tile = fmaxf(fmaxf(mrun[0], mrun[1]), fmaxf(mrun[2], mrun[3]));
-          const float m_new = fmaxf(m_used, m_tile);
-          const float tile_sum = (sum[0] + sum[1]) + (sum[2] + sum[3]);
-          const float grow = (m_new - m_used) * sl2;                  // log2 of the factor the offset is short of
-          if (attempt == 0 && __any_sync(0xffffffffu, grow > 90.f)) {
-            // pathological jump: redo this tile with its true maximum (S_t is still in TMEM, P_t not published)
-            const float alpha = fast_exp2((m_used - m_new) * sl2);
-            l = l_prev * alpha;
-            if (j > 0) scale_O(alpha * o_alpha);    // p_free(j-1) was awaited above
-            o_alpha = 1.f;
-            owe = false;
-            m_used = m_new;
-            continue;
-          }
-          l += tile_sum;
-          if (__any_sync(0xffffffffu, grow > 8.f)) {                  // lazy rescale, owed to O until PV_t(j) retires
-            const float alpha = fast_exp2((m_used - m_new) * sl2);
-            l *= alpha;
-            o_alpha *= alpha;
-            owe = true;
-            m_used = m_new;
-          }
-          break;
-        }
-        tc_wait_st();
-        tc_fence_before();
-        mbar_arrive(&s_free[t]);
-        mbar_arrive(&p_full[t]);
-      }
-      l /= o_alpha;     // a factor still owed after the last tile: out = (O * o_alpha) / l = O / (l / o_alpha)
-    } else
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(&s_full[t], j & 1);
       tc_fence_after();
@@ -417,33 +300,10 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Params p
 #pragma unroll
       for (int c = 0; c < 8; ++c) sum[c] = 0.f;
       uint32_t pk[64];
-      // ORDERED (POLY_MASK < 0, mode 13): ptxas hoists the MUFU.EX2 of the whole tile ahead of the row-sum adds and
-      // bf16 packs, so each warp ends its tile with ~150 issue slots of FADD / F2FP and no MUFU work, and the warps of
-      // a scheduler -- which run in lock-step -- leave the XU idle together.  A run-time zero derived from the partial
-      // sums of chunk k-2 is added to the exponent offset of chunk k: a true data dependency (x * 0 is not foldable
-      // under IEEE rules) that keeps at most two 16-column chunks of exponentials in flight and so interleaves the
-      // consumers with the MUFU stream.
-      float zero_dep[2] = {0.f, 0.f};
 #pragma unroll
       for (int c = 0; c < 128; c += 2) {
-        float off = neg_m;
-        if (POLY_MASK < 0) {
-          const int chunk = c >> 4;
-          if ((c & 15) == 0) {                      // snapshot of the sums of chunks < chunk, consumed by chunk + 1
-            const float partial = ((sum[0] + sum[1]) + (sum[2] + sum[3])) + ((sum[4] + sum[5]) + (sum[6] + sum[7]));
-            zero_dep[chunk & 1] = 0.f * partial;
-          }
-          off = neg_m + zero_dep[(chunk + 1) & 1];  // written at the start of chunk - 1: depends on chunks <= chunk - 2
-        }
-        const float x0 = fmaf(__uint_as_float(s[c]), sl2, off);
-        const float x1 = fmaf(__uint_as_float(s[c + 1]), sl2, off);
-        float p0, p1;
-        if (POLY_MASK > 0 && ((POLY_MASK >> ((c >> 1) & 7)) & 1)) {
-          exp2_poly_f32x2(x0, x1, p0, p1);
-        } else {
-          p0 = fast_exp2(x0);
-          p1 = fast_exp2(x1);
-        }
+        const float p0 = fast_exp2(fmaf(__uint_as_float(s[c]), sl2, neg_m));
+        const float p1 = fast_exp2(fmaf(__uint_as_float(s[c + 1]), sl2, neg_m));
         sum[c & 7] += p0;
         sum[(c + 1) & 7] += p1;
         pk[c >> 1] = pack_bf16x2(p0, p1);
@@ -505,31 +365,15 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Params p
 
 }  // namespace attn3
 
-int attention_v3_launch_blocks(const CUtensorMap& tm, int B, int S, int H, void* out, float scale_log2, int variant,
-                               int q_blocks, cudaStream_t stream);
-int attention_v3_launch(const CUtensorMap& tm, int B, int S, int H, void* out, float scale_log2, int variant,
-                        cudaStream_t stream) {
-  return attention_v3_launch_blocks(tm, B, S, H, out, scale_log2, variant, (int)ceil_div(S, 2 * attn3::BQ), stream);
-}
-
-// Only the first `q_blocks` 256-row query blocks (all keys): the main launch of the split mode-5 schedule.
-int attention_v3_launch_blocks(const CUtensorMap& tm, int B, int S, int H, void* out, float scale_log2, int variant,
-                               int q_blocks, cudaStream_t stream) {
-  // variant: 0 = mode 5, 1 = mode 6 (pipelined softmax), 2/3/4 = mode 5 with 25 % / 12.5 % / 37.5 % polynomial exp2
-  using Kernel = void (*)(const CUtensorMap, const attn3::Params);
-  static const Kernel kernels[6] = {attn3::attention_v3_kernel<false, 0>, attn3::attention_v3_kernel<true, 0>,
-                                    attn3::attention_v3_kernel<false, 0x88>, attn3::attention_v3_kernel<false, 0x80>,
-                                    attn3::attention_v3_kernel<false, 0xA4>, attn3::attention_v3_kernel<false, -1>};
-  AETHER_CHECK_ARG(variant >= 0 && variant < 6);
-  static SmemGrant grants[6];
-  AETHER_CUDA_OK(ensure_dynamic_smem(grants[variant], kernels[variant], attn3::SMEM_BYTES));
+int attention_v3_launch(const CUtensorMap& tm, int B, int S, int H, void* out, float scale_log2, cudaStream_t stream) {
+  static SmemGrant grant;
+  AETHER_CUDA_OK(ensure_dynamic_smem(grant, attn3::attention_v3_kernel, attn3::SMEM_BYTES));
   attn3::Params p;
   p.B = B; p.H = H; p.S = S;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.scale_log2 = scale_log2;
-  AETHER_CHECK_ARG(q_blocks > 0 && q_blocks <= (int)ceil_div(S, 2 * attn3::BQ));
-  dim3 grid((unsigned)q_blocks, (unsigned)H, (unsigned)B);
-  kernels[variant]<<<grid, attn3::THREADS, attn3::SMEM_BYTES, stream>>>(tm, p);
+  dim3 grid((unsigned)ceil_div(S, 2 * attn3::BQ), (unsigned)H, (unsigned)B);
+  attn3::attention_v3_kernel<<<grid, attn3::THREADS, attn3::SMEM_BYTES, stream>>>(tm, p);
   AETHER_CUDA_OK(cudaGetLastError());
   return AETHER_OK;
 }

@@ -128,10 +128,10 @@ class AetherTransformer3D(nn.Module):
         self._packed = None
         self._ws = None
         self._n_layers_override = -1
-        # kernel-mode switch (not a model hyper-parameter), set before pack(): attention kernel variant 0..12
-        # (csrc/attention*_tcgen05.cu, DESIGN.md "Attention roofline"); 5 = decoupled S/P buffers + skewed MMA
-        # schedule, 3.31 ms at S=15076 and the fastest variant timed inside the step (mode 2, fp16 P/V, is 3.21 ms
-        # isolated but has not been A/B-timed in the power-capped step).  AETHER_ATTENTION_MODE overrides it.
+        # kernel-mode switch (not a model hyper-parameter), set before pack(): attention kernel variant
+        # (csrc/attention*_tcgen05.cu, DESIGN.md "Attention roofline"): 5 = decoupled S/P buffers + skewed MMA schedule
+        # (default: 3.31 ms isolated / 3.86 ms inside the power-capped step at S=15076), 2 = fp16 P/V (3.21 ms isolated but
+        # 3.88 ms in-step: no gain), 0 = baseline.  AETHER_ATTENTION_MODE overrides it.
         import os
         self.attention_fp16_pv = int(os.environ.get("AETHER_ATTENTION_MODE", "5"))
         # QK-LayerNorm + RoPE inside the QKV GEMM epilogue (one launch less per layer; measured slower: off).  Read here,

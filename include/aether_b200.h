@@ -68,12 +68,10 @@ int aether_gemm_qkv_norm_rope_bf16(const void* A, int64_t lda, const void* W, in
 
 /* out[B,S,H*64] (bf16) = softmax(Q K^T * softmax_scale) V over qkv[B,S,3,H,64], non-causal, head_dim 64.
  * `v_fp16` is the kernel-variant id (all variants compute the same function to the tolerance of the tests):
- *   0 baseline (P aliases S)   1, 2 fp16 P/V (the V third of qkv must then hold fp16 bit patterns; 2 adds a
- *   polynomial exp2)   3 chunked two-pass softmax   4 sixteen softmax warps   5 decoupled S/P TMEM buffers
- *   (product default)   6 per-warp pipelined softmax   7 one tile per CTA, two CTAs per SM   8 64-key tiles with
- *   the S load in flight   9-11 mode 5 with 25 / 12.5 / 37.5 % polynomial exp2   12 three query tiles per CTA
- *   13 mode 5 with interleaved consumers   14 mode 5 on the complete 256-row blocks + mode 7 on the ragged rest
- *   (side stream).  Any other id returns AETHER_ERR_INVALID.
+ *   5 decoupled S / P TMEM buffers, skewed MMA schedule (product default)   0 baseline (P aliases S)
+ *   2 fp16 P/V with 40 % of the exponentials as an FMA-pipe polynomial (the V third of qkv must then hold fp16 bit
+ *   patterns).  Any other id returns AETHER_ERR_INVALID.  (Twelve further variants explored in round 1 -- none faster
+ *   inside the power-capped step -- are kept, unbuilt, under tools/experiments/attention/.)
  * Replaces F.scaled_dot_product_attention in CogVideoXAttnProcessor2_0 (pipeline :865). */
 int aether_attention_bf16(const void* qkv, void* out, int32_t B, int32_t S, int32_t H, float softmax_scale,
                           int32_t v_fp16, void* stream);
@@ -123,7 +121,7 @@ typedef struct AetherDitConfig {
   float freq_shift, norm_eps;
   int32_t ff_mult;
   int32_t attention_fp16_pv;   /* attention variant id passed to aether_attention_bf16 (5 = product default); for
-                                  ids 1 and 2 the QKV GEMM emits the V third as fp16 */
+                                  id 2 the QKV GEMM emits the V third as fp16 */
   int32_t fused_qkv_epilogue;  /* 1: QK-LayerNorm + RoPE run inside the QKV GEMM epilogue (one launch less per layer;
                                   measured slower, default 0).  Per handle -- the library reads no environment. */
 } AetherDitConfig;

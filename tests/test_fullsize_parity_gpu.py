@@ -10,8 +10,10 @@ the CFG batch of 2 whose second item starts at row 15076 (not a tile boundary).
   * all 42 layers at B = 2 against two B = 1 forwards of the same items (batch independence: the only check of the
     full-depth CFG batch the CPU cannot give in minutes);
   * the real-geometry VAE (block_out_channels 128/256/256/512, 3 layers per block, 240 x 360 px / 30 x 45 latent
-    tiles): encode of a 17 x 240 x 720 strip and decode of 5 x 30 x 90 latents -- one full tile ROW of the 41 x 480
-    x 720 workload (three tiles with their horizontal blends, two frame batches with conv caches) -- vs oracle.vae;
+    tiles): encode of a 17 x 160 x 432 strip and decode of 4 x 20 x 54 latents -- two horizontally overlapping tiles
+    of the real tile width with their blend, two frame batches with conv caches -- vs oracle.vae (sized so that the
+    fp32 oracle needs about a minute in total on the box's cores; the first version of this test used a full
+    240 x 720 tile row and spent 231 s in the oracle);
   * the three pipeline tasks at 41 x 480 x 720 (reconstruction, prediction + raymap, planning; CFG batch 2 with the
     dynamic guidance schedule, reference :832-899): shapes, dtypes, ranges, determinism and the raymap un-fold.
 
@@ -132,21 +134,21 @@ def _vae_pair(seed=1):
 def test_vae_encode_tile_row_matches_fp32_oracle():
     cfg, oracle, vae = _vae_pair()
     g = torch.Generator().manual_seed(3)
-    yy = torch.linspace(0, 1, 240)[None, None, :, None]
-    xx = torch.linspace(0, 1, 720)[None, None, None, :]
+    yy = torch.linspace(0, 1, 160)[None, None, :, None]
+    xx = torch.linspace(0, 1, 432)[None, None, None, :]
     tt = torch.linspace(0, 1, 17)[None, :, None, None]
     ph = torch.rand(3, 1, 1, 1, generator=g) * 6.28
     x = (0.6 * torch.sin(6.28 * (xx * 3 + tt) + ph) * torch.cos(6.28 * (yy * 2 - tt) + ph)
-         + 0.1 * torch.randn(3, 17, 240, 720, generator=g)).clamp(-1, 1).bfloat16()[None]
+         + 0.1 * torch.randn(3, 17, 160, 432, generator=g)).clamp(-1, 1).bfloat16()[None]
     t0 = time.perf_counter()
     with torch.no_grad():
         ref = oracle.encode(x.float()).latent_dist
     cpu_s = time.perf_counter() - t0
     post = vae.encode(x.to(DEV)).latent_dist
     got_mean = post.mode()
-    assert got_mean.shape == ref.mean.shape == (1, 16, 5, 30, 90)
+    assert got_mean.shape == ref.mean.shape == (1, 16, 5, 20, 54)
     rel, mx = _rel(got_mean, ref.mean)
-    print(f"full-geometry VAE encode 17x240x720 (3 tiles, 2 frame batches): mean rel-rms {rel:.3e}, max-abs {mx:.3e}; "
+    print(f"full-geometry VAE encode 17x160x432 (2 tiles, 2 frame batches): mean rel-rms {rel:.3e}, max-abs {mx:.3e}; "
           f"oracle {cpu_s:.1f} s")
     assert rel <= 2.5e-2, (rel, mx)
     # sample = mean + std * noise with the caller's noise stream: same generator state -> same draw as the oracle
@@ -160,20 +162,19 @@ def test_vae_encode_tile_row_matches_fp32_oracle():
 def test_vae_decode_tile_row_matches_fp32_oracle():
     cfg, oracle, vae = _vae_pair()
     g = torch.Generator().manual_seed(4)
-    z = torch.randn(1, 16, 5, 30, 90, generator=g).bfloat16()
+    z = torch.randn(1, 16, 4, 20, 54, generator=g).bfloat16()
     t0 = time.perf_counter()
     with torch.no_grad():
         ref = oracle.decode(z.float()).sample
     cpu_s = time.perf_counter() - t0
     got = vae.decode(z.to(DEV)).sample
-    assert got.shape == ref.shape == (1, 3, 17, 240, 720) and got.dtype == torch.bfloat16
+    assert got.shape == ref.shape == (1, 3, 16, 160, 432) and got.dtype == torch.bfloat16
     rel, mx = _rel(got, ref)
-    print(f"full-geometry VAE decode 5x30x90 -> 17x240x720 (3 tiles, 2 frame batches): rel-rms {rel:.3e}, "
+    print(f"full-geometry VAE decode 4x20x54 -> 16x160x432 (2 tiles, 2 frame batches): rel-rms {rel:.3e}, "
           f"max-abs {mx:.3e} (rms ref {ref.pow(2).mean().sqrt():.3f}); oracle {cpu_s:.1f} s")
     assert rel <= 2.5e-2, (rel, mx)
-    # the horizontal tile seams (latent columns 36 and 72 -> pixels 288 and 576) are not worse than the interior
-    seam = torch.cat([got[..., 280:296], got[..., 568:584]], -1), torch.cat([ref[..., 280:296], ref[..., 568:584]], -1)
-    assert _rel(*seam)[0] <= 3e-2
+    # the horizontal tile seam (latent column 36 -> pixel 288, blended over 72 px) is not worse than the interior
+    assert _rel(got[..., 288:360], ref[..., 288:360])[0] <= 3e-2
 
 
 # ---------------------------------------------------------------------------------------------------- configs 2/3/4 at full size

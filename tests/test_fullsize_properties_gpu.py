@@ -50,12 +50,14 @@ def test_attention_is_invariant_to_key_order(qkv):
     assert ((a - b).pow(2).mean().sqrt() / a.pow(2).mean().sqrt()).item() < 5e-3
 
 
-@pytest.mark.parametrize("mode", [5, 8, 12])
+@pytest.mark.parametrize("mode", [5, 0])
 def test_attention_matches_sdpa_at_full_size(qkv, mode):
     q, k, v = (qkv[:, :, i].transpose(1, 2) for i in range(3))
     ref = torch.nn.functional.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, S, H * 64).float()
     out = _ops().attention(qkv, v_fp16=mode).float()
-    assert (out - ref).abs().max().item() < 2e-3          # both round O to bf16; |O| ~ 1e-2 at this S
+    # both round O to bf16; |O| ~ 1e-2 at this S (measured max deviation 4.9e-4 = one bf16 ulp of the largest outputs)
+    assert (out - ref).abs().max().item() < 1e-3
+    assert ((out - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item() < 1e-2
 
 
 @pytest.mark.parametrize("N,K,epi", [(3 * D, D, 0), (4 * D, D, 1), (D, 4 * D, 2)])

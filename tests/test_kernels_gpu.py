@@ -120,7 +120,7 @@ def _attention_case(qkv_f32, v_fp16):
     ops = _ops()
     qkv = qkv_f32.bfloat16()
     v_ref = qkv[:, :, 2].float()
-    if v_fp16 in (1, 2):                                # modes 0 and 3 keep V in bf16
+    if v_fp16 == 2:                                     # modes 0 and 5 keep V in bf16
         vh = qkv_f32[:, :, 2].half()
         qkv.view(torch.float16)[:, :, 2] = vh          # V third carries fp16 bit patterns
         v_ref = vh.float()
@@ -131,7 +131,7 @@ def _attention_case(qkv_f32, v_fp16):
     return out, ref.transpose(1, 2).reshape(B, S, H * 64)
 
 
-@pytest.mark.parametrize("v_fp16", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14])
+@pytest.mark.parametrize("v_fp16", [0, 2, 5])
 @pytest.mark.parametrize("B,S,H", [(1, 256, 2), (1, 128, 1), (2, 318, 4), (1, 1000, 2), (1, 4276, 4)])
 def test_attention(B, S, H, v_fp16):
     g = torch.Generator(device=DEV).manual_seed(S + H)
@@ -140,7 +140,7 @@ def test_attention(B, S, H, v_fp16):
     _close(out, ref, 2 ** -6, 1e-2, f"attention B{B} S{S} H{H} fp16={v_fp16}")
 
 
-@pytest.mark.parametrize("v_fp16", [5, 8, 12, 14])
+@pytest.mark.parametrize("v_fp16", [0, 2, 5])
 @pytest.mark.parametrize("S", [1, 40, 64, 65, 128, 129, 191, 193, 256, 257, 385, 500, 512, 641])
 def test_attention_short_sequences(S, v_fp16):
     """1, 2, 3 ... key tiles: prologue / drain paths of the pipelined kernels, ragged last tile, empty second query tile."""
@@ -150,7 +150,7 @@ def test_attention_short_sequences(S, v_fp16):
     _close(out, ref, 2 ** -6, 1e-2, f"attention short S{S} mode={v_fp16}")
 
 
-@pytest.mark.parametrize("v_fp16", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14])
+@pytest.mark.parametrize("v_fp16", [0, 2, 5])
 def test_attention_large_logits(v_fp16):
     """Rows whose running max grows by more than 2^8 between key tiles exercise the lazy O (and l) rescale."""
     g = torch.Generator(device=DEV).manual_seed(11)
@@ -162,7 +162,7 @@ def test_attention_large_logits(v_fp16):
     _close(out, ref, 2 ** -6, 2e-2, f"attention large logits fp16={v_fp16}")
 
 
-@pytest.mark.parametrize("v_fp16", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14])
+@pytest.mark.parametrize("v_fp16", [0, 2, 5])
 def test_attention_peaked_and_flat_rows(v_fp16):
     """Nearly one-hot rows (large scale) and nearly uniform rows (tiny scale) in the same launch."""
     g = torch.Generator(device=DEV).manual_seed(12)
