@@ -178,3 +178,29 @@ def cfg_dpm_step(model_out, sample, coeffs, noise1, noise2=None, old_x0=None, gu
                                   ptr(old_x0), ptr(noise1), ptr(noise2), C.byref(coeffs), ptr(prev), ptr(prev32),
                                   ptr(x0), N, current_stream()), "cfg_dpm_step")
     return prev, prev32, x0
+
+
+@device_guard
+def resize_bilinear_u8(frames: torch.Tensor, H: int, W: int) -> torch.Tensor:
+    """frames uint8 CUDA [T, h, w, 3] -> uint8 [T, H, W, 3]: cv2.resize(frame, (W, H)) (INTER_LINEAR), bit for bit."""
+    lib = _lib.require_device()
+    _need(frames, torch.uint8, "frames")
+    T, h, w, c = frames.shape
+    assert c == 3
+    out = torch.empty(T, H, W, 3, dtype=torch.uint8, device=frames.device)
+    check(lib.aether_resize_bilinear_u8(ptr(frames), ptr(out), T, h, w, H, W, current_stream()), "resize_bilinear_u8")
+    return out
+
+
+@device_guard
+def u8_frames_to_model_input(frames: torch.Tensor) -> torch.Tensor:
+    """uint8 CUDA crop [F, H, W, 3] (any frame / row strides, contiguous pixels) -> bf16 [F, 3, H, W] = 2 * x / 255 - 1."""
+    lib = _lib.require_device()
+    if frames.dtype != torch.uint8 or not frames.is_cuda or frames.dim() != 4 or frames.shape[3] != 3 \
+            or frames.stride(3) != 1 or frames.stride(2) != 3:
+        raise ValueError("u8_frames_to_model_input: expected a uint8 CUDA [F, H, W, 3] view with contiguous pixels")
+    F, H, W, _ = frames.shape
+    out = torch.empty(F, 3, H, W, dtype=BF16, device=frames.device)
+    check(lib.aether_u8_frames_to_model_input(ptr(frames), frames.stride(0), frames.stride(1), ptr(out), F, H, W,
+                                              current_stream()), "u8_frames_to_model_input")
+    return out

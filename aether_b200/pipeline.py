@@ -311,6 +311,14 @@ class AetherV1PipelineCogVideoX:
 
     # ------------------------------------------------------------------ reference :451-512
     def _preprocess_image(self, image, height, width, device=None):
+        if (isinstance(image, torch.Tensor) and image.is_cuda and image.dtype == torch.uint8 and image.ndim == 4
+                and tuple(image.shape[1:]) == (height, width, 3) and height % self.vae_scale_factor_spatial == 0
+                and width % self.vae_scale_factor_spatial == 0 and image.stride(3) == 1 and image.stride(2) == 3):
+            # uint8 frames resident on the device at the target size: `/ 255` (:454-455), the identity crop / resize,
+            # the layout change, 2x - 1 and the bf16 cast in ONE kernel (bit-identical to the host path for every
+            # pixel value, tests/test_input_gpu.py)
+            from . import ops
+            return ops.u8_frames_to_model_input(image)
         if (isinstance(image, torch.Tensor) and image.is_cuda and image.is_floating_point() and image.ndim == 4
                 and tuple(image.shape[1:]) == (height, width, 3) and height % self.vae_scale_factor_spatial == 0
                 and width % self.vae_scale_factor_spatial == 0):

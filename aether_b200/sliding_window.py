@@ -481,17 +481,61 @@ def prepare_frames(images: Sequence[np.ndarray]) -> np.ndarray:
     return np.stack(out)
 
 
+def window_size(h: int, w: int) -> Tuple[int, int]:
+    """(new_h, new_w) of prepare_input (launch_aether.py:392-399): short side of the 480 x 720 window met exactly."""
+    aspect_ratio = w / h
+    return ((480, int(round(480 * aspect_ratio))) if aspect_ratio > 720 / 480 else (int(round(720 / aspect_ratio)), 720))
+
+
+def prepare_frames_device(images, device: Optional[torch.device] = None) -> torch.Tensor:
+    """`prepare_input` on the device, up to (not including) its `/ 255.0`: H x W x 3 uint8 frames (a list of equally
+    sized numpy arrays, or one uint8 array / tensor [T, H, W, 3]) are uploaded as they are (3 bytes per pixel) and
+    resized by aether_resize_bilinear_u8, which reproduces cv2.resize's INTER_LINEAR bit for bit.  Returns a uint8
+    CUDA tensor [T, new_h, new_w, 3]; `DeviceClip` turns it into the clip object the tile loop consumes."""
+    from . import ops
+    device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    if isinstance(images, torch.Tensor):
+        frames = images
+    else:
+        frames = torch.from_numpy(np.ascontiguousarray(np.stack(list(images)) if not isinstance(images, np.ndarray)
+                                                       else images))
+    if frames.dtype != torch.uint8 or frames.dim() != 4 or frames.shape[3] != 3:
+        raise ValueError("prepare_frames_device expects uint8 frames [T, H, W, 3]")
+    frames = frames.to(device).contiguous()
+    new_h, new_w = window_size(frames.shape[1], frames.shape[2])
+    return ops.resize_bilinear_u8(frames, new_h, new_w)
+
+
+class DeviceClip:
+    """The `[1, T, H, W, 3]` clip of launch_aether.py:401-403 held as uint8 on the GPU.  Indexing it like the reference
+    indexes its float64 array (`obs[0, t0:t1, h0:h1, w0:w1, :]`, :140-147) returns a uint8 CUDA view that the pipeline
+    converts to its bf16 model input in one kernel; `/ 255.0` is folded into that kernel."""
+
+    def __init__(self, frames_u8: torch.Tensor):
+        assert frames_u8.dtype == torch.uint8 and frames_u8.is_cuda and frames_u8.dim() == 4
+        self.frames = frames_u8
+        self.shape = (1,) + tuple(frames_u8.shape)
+
+    def __getitem__(self, idx):
+        b, ts, hs, ws, cs = idx
+        assert b == 0 and cs == slice(None)
+        return self.frames[ts, hs, ws]
+
+
 def disparity_to_depth(disparity: np.ndarray) -> np.ndarray:
     """launch_aether.py:347: depth_maps = np.clip(1.0 / disparity_video, 0, 1e2)."""
     return np.clip(1.0 / disparity, 0, 1e2)
 
 
 def evaluate_sequence(pipeline, frames: Sequence[np.ndarray], num_inference_step: int, seed: int, rank: int = 0,
-                      world_size: int = 1, group=None, device: Optional[torch.device] = None, **kw):
+                      world_size: int = 1, group=None, device: Optional[torch.device] = None,
+                      device_input: bool = True, **kw):
     """One sequence of the video-depth evaluation (launch_aether.py:338-347) with the tiles spread over `world_size`
-    ranks: frames -> prepare_frames -> sliding-window inference + blend -> (rgb of tile 0, disparity, depth) on the
-    blend rank ((None, None, None) elsewhere).  depth = clip(1 / disparity, 0, 100) is taken on the device."""
-    obs = prepare_frames(frames)[None]
+    ranks: frames -> prepare_input -> sliding-window inference + blend -> (rgb of tile 0, disparity, depth) on the
+    blend rank ((None, None, None) elsewhere).  depth = clip(1 / disparity, 0, 100) is taken on the device.
+    `device_input` (default): the uint8 frames are resized and fed to the tiles on the GPU (prepare_frames_device /
+    DeviceClip, same values as the host path); False keeps the reference's float64 host array."""
+    obs = DeviceClip(prepare_frames_device(frames, device)) if device_input else prepare_frames(frames)[None]
     rgb, disparity = process_with_sliding_window(pipeline, obs, num_inference_step, len(frames), seed, rank=rank,
                                                  world_size=world_size, group=group, device=device,
                                                  return_device=True, **kw)

@@ -320,6 +320,17 @@ int aether_scale_copy(double* dst, int64_t dst_s0, int64_t dst_s1, const void* s
 int aether_disparity_to_depth(double* dst, int64_t dst_s0, int64_t dst_s1, const void* src, int32_t src_is_f64,
                               int64_t src_s0, int64_t src_s1, int64_t n0, int64_t n1, int64_t n2, void* stream);
 
+/* ---------------------------------------------------------------- input side on the device
+ * aether_resize_bilinear_u8: dst[T, H, W, 3] = cv2.resize(src[t] (h x w x 3 uint8), (W, H)) with OpenCV's default
+ *   INTER_LINEAR, bit for bit (prepare_input, evaluation/video_depth/launch_aether.py:388-403, before its / 255.0).
+ * aether_u8_frames_to_model_input: dst bf16 [F, 3, H, W] = 2 * (src / 255) - 1 of a uint8 crop src[F, H, W, 3] (element
+ *   strides stride_t, stride_h; pixels contiguous): `/ 255.0`, the centre crop at the target size, the layout change,
+ *   the [-1, 1] map and the bf16 cast of pipeline :451-512 in one pass. */
+int aether_resize_bilinear_u8(const void* src, void* dst, int32_t T, int32_t h, int32_t w, int32_t H, int32_t W,
+                              void* stream);
+int aether_u8_frames_to_model_input(const void* src, int64_t stride_t, int64_t stride_h, void* dst, int32_t F, int32_t H,
+                                    int32_t W, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -175,3 +175,13 @@ def reference_sliding_window_module():
     install()
     import evaluation.video_depth.launch_aether as EVD
     return EVD
+
+
+def reference_depth_tools_module():
+    """evaluation/video_depth/tools.py imports only numpy / torch / scipy: loaded as a plain file module."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("aether_reference_depth_tools",
+                                                  str(REFERENCE_ROOT / "evaluation" / "video_depth" / "tools.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod

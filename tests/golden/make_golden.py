@@ -212,9 +212,41 @@ def make_prepare_input():
     print("prepare_input.npz", len(out))
 
 
+DEPTH_EVAL_MODES = {
+    "median": dict(max_depth=70, post_clip_max=70),
+    "scale": dict(max_depth=70, post_clip_max=70, align_with_scale=True),
+    "scale_shift_l2": dict(max_depth=70, post_clip_max=70, align_with_lstsq=True),
+    "scale_shift_lad": dict(max_depth=70, post_clip_max=70, align_with_lad2=True, max_iters=200, lr=1e-2),
+    "metric": dict(max_depth=70, post_clip_max=70, metric_scale=True),
+    "median_disp_edge_mask": dict(max_depth=70, disp_input=True, mask_edge=True, pre_clip_min=0.1, use_mask=True),
+}
+
+
+def make_depth_eval():
+    """evaluation/video_depth/tools.py:179-470 depth_evaluation on a seeded synthetic scene, every alignment the
+    evaluation scripts select (eval_depth.py:157-215) + the disparity-space / edge-mask / custom-mask options."""
+    from helpers import depth_eval_case
+    T = shim.reference_depth_tools_module()
+    pred, gt, mask = depth_eval_case()
+    out = {}
+    for name, kw in DEPTH_EVAL_MODES.items():
+        kw = dict(kw)
+        cm = mask if kw.pop("use_mask", False) else None
+        res, err, full, gt_full = T.depth_evaluation(pred.copy(), gt.copy(), custom_mask=cm, **kw)
+        keys = sorted(res)
+        out[f"{name}__keys"] = np.array(keys)
+        out[f"{name}__vals"] = np.array([float(res[k]) for k in keys], dtype=np.float64)
+        out[f"{name}__err_sum"] = np.float64(err.double().sum().item())
+        out[f"{name}__full_sum"] = np.float64(full.double().sum().item())
+    np.savez_compressed(HERE / "depth_eval.npz", **out)
+    print("depth_eval.npz", {k: out[f"{k}__vals"][:2] for k in DEPTH_EVAL_MODES})
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
-    which = sys.argv[1:] or ["rope", "scale", "sliding", "pipeline", "prepare"]
+    which = sys.argv[1:] or ["rope", "scale", "sliding", "pipeline", "prepare", "depth_eval"]
+    if "depth_eval" in which:
+        make_depth_eval()
     if "prepare" in which:
         make_prepare_input()
     if "rope" in which:

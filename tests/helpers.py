@@ -137,3 +137,17 @@ def prepare_input_frames(h, w, n=2):
     """Seeded uint8 frames for the prepare_input golden (tests/golden/make_golden.py::make_prepare_input)."""
     g = np.random.default_rng(h * 10000 + w)
     return [g.integers(0, 256, size=(h, w, 3), dtype=np.uint8) for _ in range(n)]
+
+
+def depth_eval_case(seed=0, frames=3, h=48, w=64):
+    """Seeded (prediction, ground truth, custom mask) for the depth-metric golden: a smooth scene with a depth step,
+    holes (gt = 0), far pixels beyond max_depth and a prediction that is an affine + noisy distortion of it."""
+    g = np.random.default_rng(seed)
+    yy, xx = np.meshgrid(np.linspace(0, 1, h), np.linspace(0, 1, w), indexing="ij")
+    gt = np.stack([4.0 + 30.0 * xx + 6.0 * np.sin(5 * yy + 0.7 * f) + 25.0 * (xx > 0.6) for f in range(frames)])
+    gt[:, :3, :] = 0.0
+    gt[:, -2:, -9:] = 95.0
+    pred = 0.37 * gt + 1.3 + 0.4 * g.standard_normal(gt.shape)
+    pred = np.abs(pred) + 0.05
+    mask = g.random(gt.shape) > 0.2
+    return pred.astype(np.float64), gt.astype(np.float64), mask

@@ -210,3 +210,36 @@ def test_pipeline_error_messages_match_reference(golden_dir):
         with pytest.raises(ValueError) as ei:
             pipe(**kw)
         assert str(ei.value) == str(g[k]), k
+
+
+# ------------------------------------------------------------------------------------------------ depth metrics (8f rank 4)
+def test_depth_evaluation_matches_reference(golden_dir, tmp_path):
+    """aether_b200.depth_eval.depth_evaluation against evaluation/video_depth/tools.py:179-470 run by the reference
+    itself (tests/golden/make_golden.py::make_depth_eval): every alignment eval_depth.py selects, the disparity-space /
+    edge-mask / custom-mask options, and the `frame_%04d.npy` round trip of launch_aether.py:364-365."""
+    import sys
+    sys.path.insert(0, str(golden_dir))
+    from make_golden import DEPTH_EVAL_MODES
+    from aether_b200.depth_eval import depth_evaluation, evaluate_depth_sequence, save_depth_frames
+    from helpers import depth_eval_case
+    g = np.load(golden_dir / "depth_eval.npz")
+    pred, gt, mask = depth_eval_case()
+    for name, kw in DEPTH_EVAL_MODES.items():
+        kw = dict(kw)
+        cm = mask if kw.pop("use_mask", False) else None
+        res, err, full, gt_full = depth_evaluation(pred.copy(), gt.copy(), custom_mask=cm, **kw)
+        keys = sorted(res)
+        assert keys == [str(k) for k in g[f"{name}__keys"]]
+        # identical torch / numpy operations on identical inputs; the Adam-fitted mode goes through 200 float64 updates
+        tol = 1e-9 if name != "scale_shift_lad" else 1e-6
+        np.testing.assert_allclose([float(res[k]) for k in keys], g[f"{name}__vals"], rtol=tol, atol=1e-12, err_msg=name)
+        assert err.double().sum().item() == pytest.approx(float(g[f"{name}__err_sum"]), rel=tol)
+        assert full.double().sum().item() == pytest.approx(float(g[f"{name}__full_sum"]), rel=tol)
+        assert err.shape == gt_full.shape == (pred.shape[0] * pred.shape[1], pred.shape[2])
+    # writer -> reader round trip: np.save per frame, evaluated with the `--align scale&shiftl2` selection
+    depth = np.clip(1.0 / np.maximum(pred, 1e-3), 0, 1e2)
+    assert save_depth_frames(str(tmp_path / "seq"), depth) == pred.shape[0]
+    assert sorted(p.name for p in (tmp_path / "seq").iterdir()) == [f"frame_{i:04d}.npy" for i in range(pred.shape[0])]
+    back = evaluate_depth_sequence(str(tmp_path / "seq"), list(gt), align="scale&shiftl2")
+    direct = depth_evaluation(depth, gt, max_depth=70, post_clip_max=70, align_with_lstsq=True)[0]
+    assert back == direct
