@@ -54,7 +54,8 @@ __device__ __forceinline__ double scale_from_sums(const double* sums) {
 
 // compute_scale with mask == 1 (np.ones_like, launch_aether.py:195/:272): both operands are cast to fp32
 // (`torch.from_numpy(x).float()`, postprocess_utils.py:848-851), the products are fp32; the reference sums
-// them in fp32 (torch.sum), we accumulate the same fp32 products in fp64, which is at least as accurate.
+// them in fp32 (torch.sum), we add the same fp32 products four at a time in fp32 and accumulate those in fp64, which is
+// at least as accurate.
 // Deterministic: per-block partials land in `work`, the last block to finish adds them in block order.
 // Tolerance on the resulting scale vs the reference: rel 1e-6 (tests).
 __global__ void __launch_bounds__(kBlendThreads)
@@ -73,11 +74,14 @@ scale_reduce_kernel(View3 pred, View3 target, int64_t n0, int64_t n1, int64_t n2
         p[u] = c < n2 ? ld_f32(pred, po + c) : 0.f;
         t[u] = c < n2 ? ld_f32(target, to + c) : 0.f;
       }
-#pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {      // ascending column order per thread: the summation order is fixed
-        num += double(__fmul_rn(p[u], t[u]));
-        den += double(__fmul_rn(p[u], p[u]));
-      }
+      // the four fp32 products of a pass are summed pairwise in fp32 (like one level of torch.sum's own pairwise
+      // tree), then widened: a quarter of the F2F.F64 conversions, which -- not the loads -- bounded this kernel
+      // (ncu round 2: 54 % of the copy bandwidth with a widening per product).  Fixed order => deterministic.
+      static_assert(kUnroll == 4, "pairwise tree below is written for four chunks");
+      num += double(__fadd_rn(__fadd_rn(__fmul_rn(p[0], t[0]), __fmul_rn(p[1], t[1])),
+                              __fadd_rn(__fmul_rn(p[2], t[2]), __fmul_rn(p[3], t[3]))));
+      den += double(__fadd_rn(__fadd_rn(__fmul_rn(p[0], p[0]), __fmul_rn(p[1], p[1])),
+                              __fadd_rn(__fmul_rn(p[2], p[2]), __fmul_rn(p[3], p[3]))));
     }
   }
 #pragma unroll

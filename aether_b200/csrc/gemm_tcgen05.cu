@@ -417,6 +417,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
   }
   if (warp == 1) tmem_alloc_2cta<512>(tmem_base_ptr);
   tc_fence_before();
+  __syncthreads();                                       // CTA-local ordering of the allocator's shared-memory write
+  // (compute-sanitizer racecheck still flags the cta_group::2 allocator's write against the read below: the peer CTA's
+  //  half of the collective alloc is ordered by the cluster barrier, which the tool does not model;
+  //  profiles/r2_sanitizer_racecheck_gemm2.log.  memcheck is clean.)
   cluster_sync_all();                                    // barriers of BOTH CTAs initialised before any remote signal
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_base_ptr, 0);

@@ -28,7 +28,7 @@ using namespace aether;
 
 struct ConvP { const void* w; const float* b; int kt, kh, kw, cin, cout; };
 struct NormP { const float* g; const float* b; };
-struct YbP { const void* w; const float* b; };     // fused conv_y | conv_b 1x1x1 weights [2C, L]
+struct YbP { const void* w; const float* b; int col, n; };     // fused conv_y | conv_b 1x1x1 weights [2C, L]; column offset in the concatenation
 
 class Arena {
  public:
@@ -93,6 +93,7 @@ struct AetherVae {
   std::unordered_map<std::string, ConvP> conv;
   std::unordered_map<std::string, NormP> norm;
   std::unordered_map<std::string, YbP> yb;
+  YbP yb_all{nullptr, nullptr, 0, 0};                // every decoder conv_yb row-concatenated (optional)
 };
 
 namespace {
@@ -105,6 +106,7 @@ struct Exec {
   cudaStream_t st;
   int rc = AETHER_OK;
   int64_t launches = 0;
+  char* zyb_all = nullptr;        // [rows(zq), yb_all.n] conv_y | conv_b of EVERY decoder SpatialNorm for the current batch
 
   bool dry() const { return ar->dry(); }
   bool ok() const { return rc == AETHER_OK; }
@@ -175,17 +177,25 @@ struct Exec {
     }
     auto yp = h->yb.find(name + ".conv_yb");
     if (yp == h->yb.end()) { run(AETHER_ERR_INVALID); ar->release(ws); return; }
-    // conv_y / conv_b are 1x1x1: evaluate them at LATENT resolution (they commute with nearest interpolation) as one GEMM
+    // conv_y / conv_b are 1x1x1: evaluate them at LATENT resolution (they commute with nearest interpolation) as a GEMM --
+    // one for ALL norms of the frame batch when the concatenated weights were supplied (decoder() fills zyb_all)
     const int64_t nz = zq->rows();
-    char* zyb = ar->alloc(nz * 2 * x.C * 2);
-    if (!zyb) { run(AETHER_ERR_WORKSPACE); ar->release(ws); return; }
-    ++launches;
-    if (!dry() && ok())
-      run(gemm_bf16(zq->p, zq->C, yp->second.w, zq->C, zyb, 2 * x.C, (int)nz, 2 * x.C, zq->C, yp->second.b, 0, nullptr,
-                    nullptr, 0, 0, 0, -1, st));
+    char* zyb = nullptr;
+    int zld = 2 * x.C;
+    if (zyb_all != nullptr && yp->second.n == 2 * x.C) {
+      zld = h->yb_all.n;
+    } else {
+      zyb = ar->alloc(nz * 2 * x.C * 2);
+      if (!zyb) { run(AETHER_ERR_WORKSPACE); ar->release(ws); return; }
+      ++launches;
+      if (!dry() && ok())
+        run(gemm_bf16(zq->p, zq->C, yp->second.w, zq->C, zyb, 2 * x.C, (int)nz, 2 * x.C, zq->C, yp->second.b, 0, nullptr,
+                      nullptr, 0, 0, 0, -1, st));
+    }
+    const char* zy = zyb ? zyb : zyb_all + int64_t(yp->second.col) * 2;
     IMap tmap;
     const int T = x.T, Tz = zq->T;
-    if (T > IMap::kMax) { run(AETHER_ERR_INVALID); ar->release(zyb); ar->release(ws); return; }
+    if (T > IMap::kMax) { run(AETHER_ERR_INVALID); if (zyb) ar->release(zyb); ar->release(ws); return; }
     if (T > 1 && T % 2 == 1) {       // F.interpolate of the first frame separately from the rest (odd frame counts)
       tmap.v[0] = 0;
       for (int t = 1; t < T; ++t) tmap.v[t] = 1 + ((t - 1) * (Tz - 1)) / (T - 1);
@@ -194,9 +204,9 @@ struct Exec {
     }
     ++launches;
     if (!dry() && ok())
-      run(gn_apply_imap(x.p, out, x.rows(), x.C, G, mr, np->second.g, np->second.b, zyb, zyb + int64_t(x.C) * 2, 2 * x.C,
-                        &tmap, x.H, x.W, zq->H, zq->W, 1, st));
-    ar->release(zyb);
+      run(gn_apply_imap(x.p, out, x.rows(), x.C, G, mr, np->second.g, np->second.b, zy, zy + int64_t(x.C) * 2, zld, &tmap,
+                        x.H, x.W, zq->H, zq->W, 1, st));
+    if (zyb) ar->release(zyb);
     ar->release(ws);
   }
 
@@ -331,6 +341,14 @@ struct Exec {
     const AetherVaeConfig& c = h->cfg;
     int tl = 0;
     while ((1 << tl) < c.temporal_compression_ratio) ++tl;
+    if (h->yb_all.w != nullptr) {     // every SpatialNorm's (scale | bias) table of this batch in one GEMM on the latent
+      zyb_all = ar->alloc(z.rows() * int64_t(h->yb_all.n) * 2);
+      if (!zyb_all) { run(AETHER_ERR_WORKSPACE); return Tn(); }
+      ++launches;
+      if (!dry() && ok())
+        run(gemm_bf16(z.p, z.C, h->yb_all.w, z.C, zyb_all, h->yb_all.n, (int)z.rows(), h->yb_all.n, z.C, h->yb_all.b, 0,
+                      nullptr, nullptr, 0, 0, 0, -1, st));
+    }
     Tn hcur = causal_from(z, "decoder.conv_in", cache, nc);
     for (int j = 0; j < 2 && ok(); ++j) hcur = resnet(hcur, nm("decoder.mid_block.resnets.%d", j), cache, nc, &z);
     for (int i = 0; i < c.num_blocks && ok(); ++i) {
@@ -341,6 +359,7 @@ struct Exec {
     if (!ok()) return Tn();
     Tn y = norm_conv(hcur, "decoder.norm_out", "decoder.conv_out", cache, nc, &z, nullptr, dst);
     drop(hcur);
+    if (zyb_all) { ar->release(zyb_all); zyb_all = nullptr; }
     return y;
   }
 
@@ -516,7 +535,8 @@ int aether_vae_create(const AetherVaeConfig* cfg, const AetherVaeParam* params, 
     const std::string name(p.name);
     if (p.kind == 0) h->conv[name] = ConvP{p.data, p.bias, p.kt, p.kh, p.kw, p.cin, p.cout};
     else if (p.kind == 1) h->norm[name] = NormP{reinterpret_cast<const float*>(p.data), p.bias};
-    else if (p.kind == 2) h->yb[name] = YbP{p.data, p.bias};
+    else if (p.kind == 2) h->yb[name] = YbP{p.data, p.bias, p.cin, p.cout};
+    else if (p.kind == 3) h->yb_all = YbP{p.data, p.bias, 0, p.cout};
     else { delete h; return AETHER_ERR_INVALID; }
   }
   *out = h;

@@ -307,6 +307,17 @@ class AetherVAE(nn.Module):
             stage(f"decoder.up_blocks.{i}", b, True)
         spatial("decoder.norm_out", d.norm_out)
         conv("decoder.conv_out", d.conv_out.conv)
+        # all conv_y | conv_b matrices of the decoder in ONE buffer (the individual entries become views of it): the
+        # native schedule evaluates every SpatialNorm's 1x1x1 convs of a frame batch with a single GEMM on the latent
+        yb = sorted(k for k in P if k.endswith(".conv_yb"))
+        w_all = torch.cat([P[k]["w"] for k in yb], dim=0).contiguous()
+        b_all = torch.cat([P[k]["b"] for k in yb]).contiguous()
+        off = 0
+        for k in yb:
+            n = P[k]["w"].shape[0]
+            P[k] = dict(w=w_all[off:off + n], b=b_all[off:off + n], col=off)
+            off += n
+        P["decoder.conv_yb_all"] = dict(w=w_all, b=b_all, col=0, all=True)
         self._packed = P
         self._create_handle()
         return self
@@ -356,8 +367,10 @@ class AetherVAE(nn.Module):
                 arr[i].cin, arr[i].cout = p["cin"], p["cout"]
             elif "g" in p:
                 arr[i].kind, arr[i].data, arr[i].bias = 1, p["g"].data_ptr(), p["b"].data_ptr()
-            else:
-                arr[i].kind, arr[i].data, arr[i].bias = 2, p["w"].data_ptr(), p["b"].data_ptr()
+            else:       # kind 2: one SpatialNorm's conv_y | conv_b (cin = its first column in the concatenation); kind 3: all
+                arr[i].kind = 3 if p.get("all") else 2
+                arr[i].data, arr[i].bias = p["w"].data_ptr(), p["b"].data_ptr()
+                arr[i].cin, arr[i].cout = p["col"], p["w"].shape[0]
         h = C.c_void_p()
         check(lib.aether_vae_create(C.byref(cfg), arr, len(items), C.byref(h)), "vae_create")
         self._handle, self._handle_tiling = h, bool(self.use_tiling)

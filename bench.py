@@ -383,6 +383,26 @@ def run_product(args):
                            "out on the blend rank): 8 tiles over N ranks, rgb decode skipped for tiles whose rgb the "
                            "reference discards"}
 
+    # ---- correctness of the exchange + blend at THIS world size: the reference's 24-tile golden chain (129 frames of
+    # 480 x 853, tests/golden/sliding_long.npz, produced by the reference's process_with_sliding_window) through the same
+    # tile-parallel engine with the golden's deterministic stand-in tiles; checked on the blend rank.
+    xcheck = None
+    gpath = ROOT / "tests" / "golden" / "sliding_long.npz"
+    if not args.no_exchange_check and gpath.exists():
+        sys.path.insert(0, str(ROOT / "tests"))
+        from helpers import fake_tile_outputs, subsample, synthetic_long_clip
+        gold = np.load(gpath)
+        t_, h_, w_ = gold["thw"].tolist()
+        obs = synthetic_long_clip(t_, h_, w_)
+        _, disp = process_with_sliding_window(
+            None, obs, 4, t_, 3407, rank=rank, world_size=world, device=dev,
+            tile_fn=lambda tl, crop: fake_tile_outputs(crop, tl.t_start, tl.h_start, tl.w_start))
+        if rank == 0:
+            ok = bool(np.allclose(subsample(disp, (3, 16, 16)), gold["disparity_sub"], rtol=2e-6, atol=0)
+                      and abs(disp.sum() - float(gold["disparity_sum"])) <= 2e-6 * abs(float(gold["disparity_sum"])))
+            xcheck = {"golden": "tests/golden/sliding_long.npz (24 tiles, reference-generated)", "world_size": world,
+                      "matches_rtol_2e-6": ok}
+
     if rank == 0:
         peak, peak_src = _peaks()
         flop = 4.0 * 1 * HEADS * float(S_TOKENS) ** 2 * 64
@@ -422,6 +442,8 @@ def run_product(args):
             line["config"]["INVALID_FOR_HEADLINE"] = f"--tile-steps {tile_steps} (development run; the metric needs 50)"
         if strong is not None:
             line["config5_4step"] = strong
+        if xcheck is not None:
+            line["exchange_blend_check"] = xcheck
         if world == 1 and not args.no_gpu_library_baseline:
             fwd_ms = gpu_library_forward_ms(dev)
             line["gpu_library_baseline"] = {
@@ -462,6 +484,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-library-baseline", action="store_true")
     ap.add_argument("--no-strong-leg", action="store_true", help="skip the fixed-clip 4-step strong-scaling leg")
+    ap.add_argument("--no-exchange-check", action="store_true", help="skip the golden check of the exchange + blend")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -247,7 +247,10 @@ typedef struct AetherVaeConfig {
  *   kind 0  convolution: data = bf16 [cout, kt*kh*kw*ceil64(cin)] (aether_conv3d_bf16 layout), bias fp32 [cout]
  *   kind 1  GroupNorm affine ("...norm1" for the encoder, "...norm1.norm_layer" for SpatialNorm3D): data = gamma fp32,
  *           bias = beta fp32
- *   kind 2  SpatialNorm3D conv_y | conv_b fused ("...norm1.conv_yb"): data = bf16 [2C, latent_channels], bias fp32 [2C] */
+ *   kind 2  SpatialNorm3D conv_y | conv_b fused ("...norm1.conv_yb"): data = bf16 [2C, latent_channels], bias fp32 [2C];
+ *           cin = index of its first row inside the kind-3 concatenation (0 if there is none), cout = 2C
+ *   kind 3  (optional, name free) ALL kind-2 matrices row-concatenated: data = bf16 [cout, latent_channels], bias fp32
+ *           [cout]; lets the decoder evaluate every SpatialNorm's 1x1x1 convs of a frame batch with one GEMM */
 typedef struct AetherVaeParam {
   const char* name;
   int32_t kind;

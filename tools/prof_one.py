@@ -1,5 +1,5 @@
 """Run ONE kernel family at full shape a few times (for ncu captures).
-usage: prof_one.py attention [n] [mode] | gemm | ln | qk | gemv | step | patch | blend"""
+usage: prof_one.py attention [n] [mode] | gemm | gemm_out | ln | qk | gemv | step | patch | blend"""
 import math
 import sys
 from pathlib import Path
@@ -26,6 +26,14 @@ elif which == "gemm":
     b = torch.zeros(4 * D, device="cuda")
     for _ in range(n):
         ops.gemm(a, w, b, 1)
+elif which == "gemm_out":     # to_out: N = K = 3072, gated residual epilogue in place (the GEMM furthest from cuBLAS)
+    a = torch.randn(S, D, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(D, D, device="cuda", generator=g) / math.sqrt(D)).bfloat16()
+    b = torch.zeros(D, device="cuda")
+    gv = torch.randn(1, D, device="cuda", generator=g); gt = torch.randn(1, D, device="cuda", generator=g)
+    out = torch.randn(S, D, device="cuda", generator=g).bfloat16()
+    for _ in range(n):
+        ops.gemm(a, w, b, 2, out=out, gate_vid=gv, gate_txt=gt, S=S, St=226)
 elif which == "ln":
     x = torch.randn(1, S, D, device="cuda", generator=g).bfloat16()
     gm = torch.ones(D, device="cuda"); bt = torch.zeros(D, device="cuda"); mod = torch.randn(1, 4 * D, device="cuda")
