@@ -71,6 +71,9 @@ SIGNATURES = {
                                                  c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
                                                  c_void_p, c_float, c_void_p, c_void_p, c_int32, c_void_p]),
     "aether_attention_bf16": (C.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_float, c_int32, c_void_p]),
+    "aether_attention_workspace_bytes": (c_int64, [c_int32, c_int32, c_int32, c_int32]),
+    "aether_attention_bf16_ws": (C.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_float, c_int32, c_void_p,
+                                           c_int64, c_void_p]),
     "aether_ln_modulate": (C.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p,
                                      c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                      c_void_p]),

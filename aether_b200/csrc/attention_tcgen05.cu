@@ -396,13 +396,15 @@ static int launch(const CUtensorMap& tm, const Params& p, dim3 grid, cudaStream_
 
 }  // namespace attn
 
-int attention_v3_launch(const CUtensorMap& tm, int B, int S, int H, void* out, float scale_log2, cudaStream_t stream);
+int attention_v3_launch(const CUtensorMap& tm, int B, int S, int H, void* out, float scale_log2, void* workspace,
+                        int64_t workspace_bytes, cudaStream_t stream);
+int64_t attention_v3_workspace_bytes(int B, int S, int H);
 
 // `v_fp16` is the variant id: 5 = decoupled S / P TMEM buffers (product default, attention_v3_tcgen05.cu), 0 = baseline
 // (P aliases S), 2 = fp16 P/V (the V third of qkv then holds fp16 values, GEMM f16_from_col) with 40 % of the exponentials
 // as an FMA-pipe polynomial.
-int attention_bf16(const void* qkv, void* out, int B, int S, int H, float softmax_scale, int v_fp16,
-                   cudaStream_t stream) {
+int attention_bf16_ws(const void* qkv, void* out, int B, int S, int H, float softmax_scale, int v_fp16, void* workspace,
+                      int64_t workspace_bytes, cudaStream_t stream) {
   AETHER_CHECK_ARG(B > 0 && S > 0 && H > 0);
   AETHER_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0);
   CUtensorMap tm;
@@ -419,14 +421,28 @@ int attention_bf16(const void* qkv, void* out, int B, int S, int H, float softma
   switch (v_fp16) {
     case 0: return attn::launch<0>(tm, p, grid, stream);                             // baseline: P aliases S
     case 2: return attn::launch<2>(tm, p, grid, stream);                             // fp16 P/V + 40 % polynomial exp2
-    case 5: return attention_v3_launch(tm, B, S, H, out, p.scale_log2, stream);      // decoupled S / P buffers (default)
+    case 5: return attention_v3_launch(tm, B, S, H, out, p.scale_log2, workspace, workspace_bytes, stream);   // default
     default: break;
   }
   AETHER_CHECK_ARG(!"unknown attention variant id (v_fp16 must be 0, 2 or 5)");
   return AETHER_ERR_INVALID;
 }
 
+int attention_bf16(const void* qkv, void* out, int B, int S, int H, float softmax_scale, int v_fp16,
+                   cudaStream_t stream) {
+  return attention_bf16_ws(qkv, out, B, S, H, softmax_scale, v_fp16, nullptr, 0, stream);
+}
+
 }  // namespace aether
+
+extern "C" int64_t aether_attention_workspace_bytes(int32_t B, int32_t S, int32_t H, int32_t v_fp16) {
+  return v_fp16 == 5 ? aether::attention_v3_workspace_bytes(B, S, H) : 0;
+}
+extern "C" int aether_attention_bf16_ws(const void* qkv, void* out, int32_t B, int32_t S, int32_t H, float softmax_scale,
+                                        int32_t v_fp16, void* workspace, int64_t workspace_bytes, void* stream) {
+  return aether::attention_bf16_ws(qkv, out, B, S, H, softmax_scale, v_fp16, workspace, workspace_bytes,
+                                   reinterpret_cast<cudaStream_t>(stream));
+}
 
 extern "C" int aether_attention_bf16(const void* qkv, void* out, int32_t B, int32_t S, int32_t H,
                                      float softmax_scale, int32_t v_fp16, void* stream) {

@@ -29,6 +29,14 @@ struct Params {
   int B, H, S;
   __nv_bfloat16* out;
   float scale_log2;
+  // Work decomposition (1-D grid).  CTA c works on item = item_begin + c / kv_splits, an item being one 256-row query
+  // block of one head (q_blk fastest, then head, then batch); with kv_splits > 1 it only visits key tiles
+  // [split * kv_chunk, (split + 1) * kv_chunk) and leaves an UNNORMALISED partial (O fp32, row max, row sum) in
+  // part_o / part_ml for attention_combine_kernel -- the tail wave of the grid is cut along the keys so that it fills
+  // every SM instead of 20 of 148 (see the launcher).
+  int q_blocks, item_begin, kv_splits, kv_chunk;
+  float* part_o;       // [ctas][256][64]
+  float* part_ml;      // [ctas][256][2]
 };
 
 // Round-1 variants of this kernel (per-warp pipelined softmax, 12.5-37.5 % of the exponentials on the FMA pipe,
@@ -56,10 +64,14 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Params p
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform: uniform-datapath MMA issue
   const int lane = threadIdx.x & 31;
-  const int q_blk = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int q0 = q_blk * 2 * BQ;
-  const int n_kv = (p.S + BKV - 1) / BKV;
   const int H = p.H;
+  const int item = p.item_begin + int(blockIdx.x) / p.kv_splits;
+  const int split = int(blockIdx.x) % p.kv_splits;
+  const int q_blk = item % p.q_blocks, h = (item / p.q_blocks) % H, b = item / (p.q_blocks * H);
+  const int q0 = q_blk * 2 * BQ;
+  const int n_kv_total = (p.S + BKV - 1) / BKV;
+  const int kv_t0 = p.kv_splits > 1 ? split * p.kv_chunk : 0;                    // first key tile of this CTA
+  const int n_kv = p.kv_splits > 1 ? min(p.kv_chunk, n_kv_total - kv_t0) : n_kv_total;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_qkv);
@@ -105,14 +117,14 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Params p
         mbar_wait(&k_empty[ks], kph ^ 1);
         if (lead) {
           mbar_arrive_expect_tx(&k_full[ks], TILE_BYTES);
-          tma_load_4d(smem_k + ks * TILE_BYTES, &tmap_qkv, &k_full[ks], 0, H + h, j * BKV, b);
+          tma_load_4d(smem_k + ks * TILE_BYTES, &tmap_qkv, &k_full[ks], 0, H + h, (kv_t0 + j) * BKV, b);
         }
         __syncwarp();
         if (++ks == KSTAGES) { ks = 0; kph ^= 1; }
         mbar_wait(&v_empty[vs], vph ^ 1);
         if (lead) {
           mbar_arrive_expect_tx(&v_full[vs], TILE_BYTES);
-          tma_load_4d(smem_v + vs * TILE_BYTES, &tmap_qkv, &v_full[vs], 0, 2 * H + h, j * BKV, b);
+          tma_load_4d(smem_v + vs * TILE_BYTES, &tmap_qkv, &v_full[vs], 0, 2 * H + h, (kv_t0 + j) * BKV, b);
         }
         __syncwarp();
         if (++vs == VSTAGES) { vs = 0; vph ^= 1; }
@@ -258,7 +270,7 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Params p
       tc_wait_ld();
       tc_fence_before();
       mbar_arrive(&s_free[t]);                     // S_t may be overwritten by QK_t(j+1) from now on
-      const int kv_valid = p.S - j * BKV;
+      const int kv_valid = p.S - (kv_t0 + j) * BKV;
       if (kv_valid < BKV) {
 #pragma unroll
         for (int c = 0; c < 128; ++c)
@@ -331,7 +343,20 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Params p
     tmem_ld_32x32b_x32(o_addr + 32, o1);
     tc_wait_ld();
     const int row = q0 + t * BQ + row_in_tile;
-    if (row < p.S) {
+    if (p.kv_splits > 1) {
+      // partial result of this key range: O (relative to the offset m_used), m_used and l, combined later
+      float4* po = reinterpret_cast<float4*>(p.part_o + (int64_t(blockIdx.x) * 2 * BQ + t * BQ + row_in_tile) * DH);
+#pragma unroll
+      for (int v = 0; v < 8; ++v)
+        po[v] = make_float4(__uint_as_float(o0[4 * v]), __uint_as_float(o0[4 * v + 1]), __uint_as_float(o0[4 * v + 2]),
+                            __uint_as_float(o0[4 * v + 3]));
+#pragma unroll
+      for (int v = 0; v < 8; ++v)
+        po[8 + v] = make_float4(__uint_as_float(o1[4 * v]), __uint_as_float(o1[4 * v + 1]), __uint_as_float(o1[4 * v + 2]),
+                                __uint_as_float(o1[4 * v + 3]));
+      *reinterpret_cast<float2*>(p.part_ml + (int64_t(blockIdx.x) * 2 * BQ + t * BQ + row_in_tile) * 2) =
+          make_float2(m_used, l);
+    } else if (row < p.S) {
       const float inv = 1.0f / l;
       __nv_bfloat16* dst = p.out + (int64_t(b) * p.S + row) * (int64_t(H) * DH) + h * DH;
 #pragma unroll
@@ -363,17 +388,92 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Params p
   }
 }
 
+
+// out[row, h*64 + c] = sum_i O_i[c] * w_i / sum_i l_i * w_i,  w_i = 2^((m_i - max_j m_j) * scale_log2): the flash-attention
+// merge of the `splits` key-range partials of one item.  One warp per query row, two columns per lane.
+__global__ void __launch_bounds__(256)
+attention_combine_kernel(const Params p, int n_items) {
+  const int lane = threadIdx.x & 31;
+  const int wrow = (blockIdx.x * 256 + threadIdx.x) >> 5;           // global (item, row) index
+  if (wrow >= n_items * 2 * BQ) return;
+  const int it = wrow / (2 * BQ), r = wrow - it * (2 * BQ);
+  const int item = p.item_begin + it;
+  const int q_blk = item % p.q_blocks, h = (item / p.q_blocks) % p.H, b = item / (p.q_blocks * p.H);
+  const int row = q_blk * 2 * BQ + r;
+  if (row >= p.S) return;
+  float m = -INFINITY;
+  for (int i = 0; i < p.kv_splits; ++i)
+    m = fmaxf(m, p.part_ml[((int64_t(it) * p.kv_splits + i) * 2 * BQ + r) * 2]);
+  float l = 0.f, a0 = 0.f, a1 = 0.f;
+  for (int i = 0; i < p.kv_splits; ++i) {
+    const int64_t base = (int64_t(it) * p.kv_splits + i) * 2 * BQ + r;
+    const float2 ml = *reinterpret_cast<const float2*>(p.part_ml + base * 2);
+    const float w = fast_exp2((ml.x - m) * p.scale_log2);
+    const float2 o = *reinterpret_cast<const float2*>(p.part_o + base * DH + 2 * lane);
+    l = fmaf(ml.y, w, l);
+    a0 = fmaf(o.x, w, a0);
+    a1 = fmaf(o.y, w, a1);
+  }
+  const float inv = 1.0f / l;
+  __nv_bfloat16* dst = p.out + (int64_t(b) * p.S + row) * (int64_t(p.H) * DH) + h * DH + 2 * lane;
+  *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(a0 * inv, a1 * inv);
+}
+
 }  // namespace attn3
 
-int attention_v3_launch(const CUtensorMap& tm, int B, int S, int H, void* out, float scale_log2, cudaStream_t stream) {
+// Scratch for the split tail: (items % #SM) x splits CTAs x 256 rows x (64 + 2) floats; 0 when the grid divides evenly.
+int64_t attention_v3_workspace_bytes(int B, int S, int H) {
+  const int nsm = num_sms();
+  if (nsm <= 0) return 0;
+  const int64_t items = ceil_div(S, 2 * attn3::BQ) * int64_t(H) * B;
+  const int rem = int(items % nsm);
+  if (items <= nsm || rem == 0) return 0;
+  const int splits = nsm / rem;
+  if (splits < 2) return 0;
+  return int64_t(rem) * splits * 2 * attn3::BQ * (attn3::DH + 2) * 4 + 256;
+}
+
+// One launch covers the items that fill whole waves (one CTA per SM, so a "wave" is #SM items); the remaining
+// items % #SM would occupy that many SMs for a full item time while the others idle -- at S = 15076, H = 48 that is 20 of
+// 148 SMs for the 20th of 19.14 waves (4.3 % of the kernel).  With scratch they run in a second launch cut along the keys
+// into floor(#SM / rem) ranges each (7 x 17 key tiles) and a small merge kernel, so the tail costs ~1/7 of an item time.
+int attention_v3_launch(const CUtensorMap& tm, int B, int S, int H, void* out, float scale_log2, void* workspace,
+                        int64_t workspace_bytes, cudaStream_t stream) {
   static SmemGrant grant;
   AETHER_CUDA_OK(ensure_dynamic_smem(grant, attn3::attention_v3_kernel, attn3::SMEM_BYTES));
   attn3::Params p;
   p.B = B; p.H = H; p.S = S;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.scale_log2 = scale_log2;
-  dim3 grid((unsigned)ceil_div(S, 2 * attn3::BQ), (unsigned)H, (unsigned)B);
-  attn3::attention_v3_kernel<<<grid, attn3::THREADS, attn3::SMEM_BYTES, stream>>>(tm, p);
+  p.q_blocks = (int)ceil_div(S, 2 * attn3::BQ);
+  p.item_begin = 0; p.kv_splits = 1; p.kv_chunk = 0; p.part_o = nullptr; p.part_ml = nullptr;
+  const int64_t items = int64_t(p.q_blocks) * H * B;
+  const int nsm = num_sms();
+  const int n_kv = (int)ceil_div(S, attn3::BKV);
+  const int rem = int(items % nsm);
+  int splits = (items > nsm && rem != 0) ? nsm / rem : 1;
+  if (splits > n_kv) splits = n_kv;
+  const int64_t need = int64_t(rem) * splits * 2 * attn3::BQ * (attn3::DH + 2) * 4 + 256;
+  if (splits < 2 || workspace == nullptr || workspace_bytes < need) {
+    attn3::attention_v3_kernel<<<(unsigned)items, attn3::THREADS, attn3::SMEM_BYTES, stream>>>(tm, p);
+    AETHER_CUDA_OK(cudaGetLastError());
+    return AETHER_OK;
+  }
+  const int64_t full = items - rem;
+  attn3::attention_v3_kernel<<<(unsigned)full, attn3::THREADS, attn3::SMEM_BYTES, stream>>>(tm, p);
+  attn3::Params q = p;
+  q.item_begin = (int)full;
+  q.kv_splits = splits;
+  q.kv_chunk = (int)ceil_div(n_kv, splits);
+  if (int64_t(q.kv_chunk) * (splits - 1) >= n_kv) {          // the last range must not be empty
+    q.kv_splits = splits = (int)ceil_div(n_kv, q.kv_chunk);
+  }
+  char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+  q.part_o = reinterpret_cast<float*>(base);
+  q.part_ml = q.part_o + int64_t(rem) * splits * 2 * attn3::BQ * attn3::DH;
+  attn3::attention_v3_kernel<<<(unsigned)(rem * splits), attn3::THREADS, attn3::SMEM_BYTES, stream>>>(tm, q);
+  const int warps = rem * 2 * attn3::BQ;
+  attn3::attention_combine_kernel<<<(unsigned)ceil_div(int64_t(warps) * 32, 256), 256, 0, stream>>>(q, rem);
   AETHER_CUDA_OK(cudaGetLastError());
   return AETHER_OK;
 }

@@ -20,8 +20,9 @@ int gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, i
 int gemm_qkv_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* qkv, int rows, int K, const float* bias,
                   int S, int St, int H, const float* gq, const float* bq, const float* gk, const float* bk, float eps,
                   const float* cosb, const float* sinb, int f16_from_col, cudaStream_t stream);
-int attention_bf16(const void* qkv, void* out, int B, int S, int H, float softmax_scale, int v_fp16,
-                   cudaStream_t stream);
+int attention_bf16_ws(const void* qkv, void* out, int B, int S, int H, float softmax_scale, int v_fp16, void* workspace,
+                      int64_t workspace_bytes, cudaStream_t stream);
+int64_t attention_v3_workspace_bytes(int B, int S, int H);
 int ln_modulate(const void* x, void* y, int B, int S, int St, int D, const float* gamma, const float* beta, float eps,
                 const float* gamma2, const float* beta2, const float* shift_vid, const float* scale_vid,
                 const float* shift_txt, const float* scale_txt, int64_t mod_bstride, cudaStream_t stream);
@@ -61,6 +62,8 @@ struct Workspace {
   float* temb_h;   // fp32 [B, T]
   float* temb;     // fp32 [B, T]
   float* mod;      // fp32 [B, (12L+2) D]
+  char* attn_ws;   // scratch of the attention kernel's split tail wave (may be empty)
+  int64_t attn_ws_bytes;
   int64_t total;
 };
 
@@ -83,6 +86,8 @@ Workspace carve(const AetherDitConfig& c, int B, int S, char* base) {
   ws.temb_h = reinterpret_cast<float*>(take(int64_t(B) * c.time_embed_dim * 4));
   ws.temb = reinterpret_cast<float*>(take(int64_t(B) * c.time_embed_dim * 4));
   ws.mod = reinterpret_cast<float*>(take(int64_t(B) * (12 * int64_t(c.num_layers) + 2) * D * 4));
+  ws.attn_ws_bytes = c.attention_fp16_pv == 5 ? aether::attention_v3_workspace_bytes(B, S, c.num_heads) : 0;
+  ws.attn_ws = take(ws.attn_ws_bytes);
   ws.total = off;
   return ws;
 }
@@ -244,7 +249,8 @@ static int dit_forward_impl(AetherDit* h, const void* in0, int C0, int B0, const
                        stream));
     }
     if (h->timing) AETHER_CUDA_OK(cudaEventRecord(h->ev[2 * l], stream));
-    RUN(attention_bf16(ws.qkv, ws.attn, B, S, c.num_heads, softmax_scale, c.attention_fp16_pv, stream));
+    RUN(attention_bf16_ws(ws.qkv, ws.attn, B, S, c.num_heads, softmax_scale, c.attention_fp16_pv,
+                          ws.attn_ws_bytes > 0 ? ws.attn_ws : nullptr, ws.attn_ws_bytes, stream));
     if (h->timing) {
       AETHER_CUDA_OK(cudaEventRecord(h->ev[2 * l + 1], stream));
       h->ev_used = l + 1;

@@ -49,16 +49,23 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
 
 
 @device_guard
-def attention(qkv: torch.Tensor, scale: Optional[float] = None, v_fp16: bool = False) -> torch.Tensor:
-    """qkv [B,S,3,H,64] bf16 -> out [B,S,H*64] bf16.  With v_fp16 the V third holds fp16 bit patterns
-    (`qkv.view(torch.float16)[:, :, 2] = v.half()`) and the fp16-PV kernel mode runs."""
+def attention(qkv: torch.Tensor, scale: Optional[float] = None, v_fp16: int = 5, split_tail: bool = True) -> torch.Tensor:
+    """qkv [B,S,3,H,64] bf16 -> out [B,S,H*64] bf16.  `v_fp16` = kernel variant (5 default, 0 baseline, 2 fp16 P/V: the V
+    third then holds fp16 bit patterns, `qkv.view(torch.float16)[:, :, 2] = v.half()`).  `split_tail` hands the kernel
+    the scratch it needs to cut the last, partially filled wave of its grid along the keys (variant 5 only)."""
     lib = _lib.require_device()
     _need(qkv, BF16, "qkv")
     B, S, three, H, dh = qkv.shape
     assert three == 3 and dh == 64
     out = torch.empty(B, S, H * dh, dtype=BF16, device=qkv.device)
-    check(lib.aether_attention_bf16(ptr(qkv), ptr(out), B, S, H, float(scale if scale is not None else dh ** -0.5),
-                                    int(v_fp16), current_stream()), "attention_bf16")
+    sc = float(scale if scale is not None else dh ** -0.5)
+    need = lib.aether_attention_workspace_bytes(B, S, H, int(v_fp16)) if split_tail else 0
+    if need > 0:
+        ws = torch.empty(need, dtype=torch.uint8, device=qkv.device)
+        check(lib.aether_attention_bf16_ws(ptr(qkv), ptr(out), B, S, H, sc, int(v_fp16), ptr(ws), need, current_stream()),
+              "attention_bf16_ws")
+    else:
+        check(lib.aether_attention_bf16(ptr(qkv), ptr(out), B, S, H, sc, int(v_fp16), current_stream()), "attention_bf16")
     return out
 
 

@@ -311,6 +311,9 @@ class AetherV1PipelineCogVideoX:
 
     # ------------------------------------------------------------------ reference :451-512
     def _preprocess_image(self, image, height, width, device=None):
+        if (isinstance(image, np.ndarray) and image.dtype == np.uint8 and image.ndim == 4 and device is not None
+                and torch.device(device).type == "cuda" and tuple(image.shape[1:]) == (height, width, 3)):
+            image = torch.from_numpy(np.ascontiguousarray(image)).to(device)      # 3 bytes per pixel cross PCIe
         if (isinstance(image, torch.Tensor) and image.is_cuda and image.dtype == torch.uint8 and image.ndim == 4
                 and tuple(image.shape[1:]) == (height, width, 3) and height % self.vae_scale_factor_spatial == 0
                 and width % self.vae_scale_factor_spatial == 0 and image.stride(3) == 1 and image.stride(2) == 3):

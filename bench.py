@@ -19,9 +19,10 @@ ROUNDS; one bench "step" = one round:
 At N = 1 a step is therefore exactly one configs[1] generation (plus its share of the blend); the clip grows with N
 (one tile per rank per round) => "scaling": "weak"; value = N * 11 latent frames * K / seconds.
   value : tile crops already resident in HBM, CUDA events around exactly K rounds, max over ranks.
-  e2e   : the same round with HOST buffers: the crop is host numpy float64 (what the reference's prepare_input hands
-          over, launch_aether.py:388-403), uploaded inside the timed region, and the frames of the blended disparity
-          that became final in the round are copied back to host numpy.
+  e2e   : the same round with HOST buffers: the tile's frames are host numpy uint8 (a decoded video), uploaded inside the
+          timed region (the reference's prepare_input would turn them into float64 on the host first,
+          launch_aether.py:388-403; same values, 8x the bytes), and the frames of the blended disparity that became
+          final in the round are copied back to host numpy.
   collective_ms / blend_ms : device-timed inside the timed rounds (blend rank), reported per round.
   config5_4step : the reference's own evaluation setting (4 denoise steps per tile, launch_aether.py:67-70) on a
           FIXED 8-tile clip at every N (strong scaling): seconds for the whole evaluate (tiles + exchange + blend +
@@ -207,7 +208,7 @@ class SyntheticClip:
         key = (n, hh, ww)
         if self.host_mode:              # one host crop per shape, generated OUTSIDE the timed region (prepare_host)
             if ("host",) + key not in self._cache:
-                self._cache[("host",) + key] = np.random.default_rng(seed).random((n, hh, ww, 3))   # float64 in [0, 1)
+                self._cache[("host",) + key] = np.random.default_rng(seed).integers(0, 256, (n, hh, ww, 3), dtype=np.uint8)
             return self._cache[("host",) + key]
         if key not in self._cache:      # one resident crop per shape: "inputs already resident in HBM"
             g = torch.Generator(device=self.device).manual_seed(seed)
@@ -342,7 +343,7 @@ def run_product(args):
     pinned = (torch.empty((WINDOW + STRIDE_T * world, CLIP_H, CLIP_W), dtype=torch.float64).pin_memory()
               if rank == 0 else None)
     run.fetch_finalized(pinned)                            # frames finalised before the e2e rounds are not counted
-    h2d = WINDOW * 480 * 720 * 3 * 8
+    h2d = WINDOW * 480 * 720 * 3              # uint8 frames of the tile
     d2h = 0
     barrier()
     t0 = time.perf_counter()
@@ -356,10 +357,10 @@ def run_product(args):
     e2e = {"value": world * LATENT_FRAMES * n_e2e * (tile_steps / DENOISE_STEPS) / e2e_s, "unit": "latent-frames/s",
            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h / n_e2e), "seconds_per_round": e2e_s / n_e2e,
            "rounds": n_e2e,
-           "scope": "one round through the public API with HOST buffers: host numpy float64 crop [41,480,720,3] -> "
-                    "AetherV1PipelineCogVideoX.__call__ (upload, preprocess, VAE encode, 50 x (DiT + DPM step), rgb + "
-                    "disparity VAE decode) -> NCCL p2p exchange -> blend chain -> D2H of the frames finalised by the round "
-                    "(bytes per round, blend rank)"}
+           "scope": "one round through the public API with HOST buffers: host numpy uint8 frames [41,480,720,3] -> "
+                    "AetherV1PipelineCogVideoX.__call__ (upload, /255 + layout + 2x-1 + bf16 in one kernel, VAE encode, "
+                    "50 x (DiT + DPM step), rgb + disparity VAE decode) -> NCCL p2p exchange -> blend chain -> D2H of the "
+                    "frames finalised by the round (bytes per round, blend rank)"}
     run.finish()                                           # complete the chain (last window already pushed)
     clip.host_mode = False
 
@@ -379,9 +380,9 @@ def run_product(args):
         strong = {"tiles": 8, "frames": sclip.shape[1], "denoise_steps_per_tile": 4, "seconds": s_s,
                   "value": 8 * LATENT_FRAMES / s_s, "unit": "latent-frames/s (4-step tiles)", "scaling": "strong",
                   "blend_rank_ms": {k: round(v, 3) for k, v in sstats.items() if k.endswith("_ms")},
-                  "scope": "evaluate one 65-frame 480x853 clip end to end (host float64 frames in, blended fp64 disparity "
-                           "out on the blend rank): 8 tiles over N ranks, rgb decode skipped for tiles whose rgb the "
-                           "reference discards"}
+                  "scope": "evaluate one 65-frame 480x853 clip end to end (host uint8 frames in, blended fp64 disparity out "
+                           "on the blend rank): 8 tiles over N ranks, rgb decode skipped for tiles whose rgb the reference "
+                           "discards"}
 
     # ---- correctness of the exchange + blend at THIS world size: the reference's 24-tile golden chain (129 frames of
     # 480 x 853, tests/golden/sliding_long.npz, produced by the reference's process_with_sliding_window) through the same

@@ -75,6 +75,13 @@ int aether_gemm_qkv_norm_rope_bf16(const void* A, int64_t lda, const void* W, in
  * Replaces F.scaled_dot_product_attention in CogVideoXAttnProcessor2_0 (pipeline :865). */
 int aether_attention_bf16(const void* qkv, void* out, int32_t B, int32_t S, int32_t H, float softmax_scale,
                           int32_t v_fp16, void* stream);
+/* Same with caller-provided scratch (aether_attention_workspace_bytes; 0 = none needed): variant 5 then cuts the LAST,
+ * partially filled wave of its grid -- (query blocks x heads x batch) % #SM work items, 20 of 148 SMs busy for a whole
+ * item time at S = 15076, H = 48 -- along the keys so that it fills every SM, and merges the partial (O, max, sum)
+ * triples with a small kernel.  Results agree with the unsplit call to fp32 merge round-off. */
+int64_t aether_attention_workspace_bytes(int32_t B, int32_t S, int32_t H, int32_t v_fp16);
+int aether_attention_bf16_ws(const void* qkv, void* out, int32_t B, int32_t S, int32_t H, float softmax_scale,
+                             int32_t v_fp16, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------- bandwidth-bound DiT kernels */
 

@@ -60,6 +60,25 @@ def test_attention_matches_sdpa_at_full_size(qkv, mode):
     assert ((out - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item() < 1e-2
 
 
+def test_attention_split_tail_wave_equals_unsplit(qkv):
+    """2832 work items on 148 SMs leave a 20-item tail wave; with scratch those items are cut into 7 key ranges and merged
+    (csrc/attention_v3_tcgen05.cu launcher).  Same function: only the fp32 merge order of the affected rows differs."""
+    from aether_b200 import _lib
+    ops = _ops()
+    assert _lib.load().aether_attention_workspace_bytes(B, S, H, 5) > 0
+    a = ops.attention(qkv, v_fp16=5, split_tail=True).float()
+    b = ops.attention(qkv, v_fp16=5, split_tail=False).float()
+    assert (a - b).abs().max().item() < 2e-4                        # |O| ~ 1e-2: well inside one bf16 ulp of the outputs
+    changed = (a != b).any(dim=2).sum().item()                      # rows that took the split path: 20 items x 256 rows
+    assert 0 < changed <= 20 * 256
+    # other remainders: 176 items -> 28-item tail in 5 key ranges; 160 items -> 12-item tail, ranges clamped to the 9 key
+    # tiles; grids smaller than one wave (no split)
+    for B2, S2, H2 in ((1, 2600, 16), (1, 1100, 32), (2, 1000, 4), (1, 300, 2)):
+        g = torch.Generator(device=DEV).manual_seed(S2)
+        x = torch.randn(B2, S2, 3, H2, 64, device=DEV, generator=g).bfloat16()
+        assert (ops.attention(x, split_tail=True).float() - ops.attention(x, split_tail=False).float()).abs().max() < 2e-3
+
+
 @pytest.mark.parametrize("N,K,epi", [(3 * D, D, 0), (4 * D, D, 1), (D, 4 * D, 2)])
 def test_gemm_full_shapes_against_fp32_matmul(N, K, epi):
     ops = _ops()
