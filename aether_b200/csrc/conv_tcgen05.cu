@@ -192,6 +192,17 @@ conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
         const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * BN + ch * CW;
         tmem_ld_32x32b_x32(taddr, v0);
         if (CW > 32) tmem_ld_32x32b_x32(taddr + 32, v1);
+        // residual (resnet skip connection): all 16-byte loads of this thread's row are issued before the TMEM wait
+        // instead of one per 8-channel group between dependent math (same finding as the GEMM's gated-residual epilogue)
+        uint4 rres[CW / 8];
+        if (p.resid != nullptr) {
+#pragma unroll
+          for (int g8 = 0; g8 < CW / 8; ++g8) {
+            const int n = n0 + g8 * 8;
+            rres[g8] = (pos_ok && n < p.Cout) ? *reinterpret_cast<const uint4*>(p.resid + pos * p.Cout + n)
+                                              : make_uint4(0u, 0u, 0u, 0u);
+          }
+        }
         tc_wait_ld();
         uint32_t packed[32];
 #pragma unroll
@@ -211,7 +222,7 @@ conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
             xv[4] += b1.x; xv[5] += b1.y; xv[6] += b1.z; xv[7] += b1.w;
           }
           if (p.resid != nullptr && pos_ok && col_ok) {
-            const uint4 r = *reinterpret_cast<const uint4*>(p.resid + pos * p.Cout + n);
+            const uint4 r = rres[g8];
             xv[0] += bf16_lo(r.x); xv[1] += bf16_hi(r.x); xv[2] += bf16_lo(r.y); xv[3] += bf16_hi(r.y);
             xv[4] += bf16_lo(r.z); xv[5] += bf16_hi(r.z); xv[6] += bf16_lo(r.w); xv[7] += bf16_hi(r.w);
           }

@@ -90,6 +90,19 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const CUtensorMap
     const uint32_t taddr = taddr_tile + ch * CCHUNK;
     tmem_ld_32x32b_x32(taddr, v0);
     tmem_ld_32x32b_x32(taddr + 32, v1);
+    // Gated-residual epilogue: the thread's 128 bytes of residual (its row, this chunk's 64 columns) are requested as
+    // eight independent 16-byte loads BEFORE anything waits, together with the TMEM load.  They used to be issued one
+    // per 8-column group between dependent math (ncu round 2, to_out shape: eight serial L2 latencies per chunk, tensor
+    // pipe 68 % of the active cycles because the MMA warp waited for the epilogue to release its accumulator).
+    uint4 resid[CCHUNK / 8];
+    if (EPI == 2) {
+#pragma unroll
+      for (int g8 = 0; g8 < CCHUNK / 8; ++g8) {
+        const int n = n0 + g8 * 8;
+        resid[g8] = (row_ok && n < p.N) ? *reinterpret_cast<const uint4*>(p.C + int64_t(row) * p.ldc + n)
+                                        : make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
     tc_wait_ld();
 
     uint32_t packed[32];
@@ -183,7 +196,7 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const CUtensorMap
         if (row_ok && col_ok) {
           const float4 g0 = __ldg(reinterpret_cast<const float4*>(gate + n));
           const float4 g1 = __ldg(reinterpret_cast<const float4*>(gate + n + 4));
-          const uint4 r = *reinterpret_cast<const uint4*>(p.C + int64_t(row) * p.ldc + n);
+          const uint4 r = resid[g8];
           x[0] = bf16_lo(r.x) + g0.x * x[0]; x[1] = bf16_hi(r.x) + g0.y * x[1];
           x[2] = bf16_lo(r.y) + g0.z * x[2]; x[3] = bf16_hi(r.y) + g0.w * x[3];
           x[4] = bf16_lo(r.z) + g1.x * x[4]; x[5] = bf16_hi(r.z) + g1.y * x[5];

@@ -37,8 +37,22 @@ q, k, v = (qkv[:, :, i].transpose(1, 2) for i in range(3))
 ref = torch.nn.functional.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, S, H * 64)
 sd, _ = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(q, k, v))
 print(json.dumps(dict(impl="torch_sdpa", ms=sd, tflops=flops / sd / 1e9)), flush=True)
+from aether_b200 import _lib  # noqa: E402
+from aether_b200._lib import check, current_stream, ptr  # noqa: E402
+lib = _lib.load()
 for m in modes:
-    out = ops.attention(qkv, v_fp16=m)
-    err = (out.float() - ref.float()).abs().max().item()
-    med, best = timeit(lambda: ops.attention(qkv, v_fp16=m))
-    print(json.dumps(dict(mode=m, ms=med, ms_best=best, tflops=flops / med / 1e9, max_abs_vs_sdpa=err)), flush=True)
+    if m == 2:                                          # fp16 P/V variant: V third re-encoded as fp16
+        qkv.view(torch.float16)[:, :, 2] = qkv[:, :, 2].float().half()
+    for split in ((True, False) if m == 5 else (False,)):
+        need = lib.aether_attention_workspace_bytes(B, S, H, m) if split else 0
+        ws = torch.empty(max(need, 1), dtype=torch.uint8, device=DEV)       # allocated once: the timing is the kernels only
+        out = torch.empty(B, S, H * 64, dtype=torch.bfloat16, device=DEV)
+
+        def run():
+            check(lib.aether_attention_bf16_ws(ptr(qkv), ptr(out), B, S, H, 0.125, m, ptr(ws) if need else 0, need,
+                                               current_stream()), "attention")
+        run()
+        err = (out.float() - ref.float()).abs().max().item()
+        med, best = timeit(run)
+        print(json.dumps(dict(mode=m, split_tail=bool(need), ms=med, ms_best=best, tflops=flops / med / 1e9,
+                              max_abs_vs_sdpa=err)), flush=True)
