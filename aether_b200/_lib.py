@@ -122,6 +122,7 @@ SIGNATURES = {
                                     c_void_p, c_int64, c_void_p]),
     "aether_vae_decode": (C.c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32, c_int32, c_int32, c_void_p,
                                     c_void_p, c_int64, c_void_p]),
+    "aether_project_points": (C.c_int, [c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
     "aether_resize_bilinear_u8": (C.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "aether_u8_frames_to_model_input": (C.c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int32, c_int32, c_int32,
                                                   c_void_p]),

@@ -87,6 +87,35 @@ u8_frames_to_model_input_kernel(const uint8_t* __restrict__ src, int64_t sT, int
   }
 }
 
+// world[t, y, x, :] = P_t[:, :3] . (depth * ((x + 0.5) * a + b, (y + 0.5) * c + d, 1)) + P_t[:, 3],  depth = 1 / clip(disp, 1e-8, 1e8)
+// (scripts/demo.py:404-420 + aether/utils/postprocess_utils.py:381-403 `project`): cam[t] = {1/f, -cx/f, 1/f, -cy/f, P (3 x 4
+// row-major)} as 16 doubles.  fp64 like the numpy path; 4|8 B read + 24 B written per pixel.
+__global__ void __launch_bounds__(256)
+project_points_kernel(const void* __restrict__ disp, int disp_f64, const double* __restrict__ cam, double* __restrict__ out,
+                      int T, int H, int W) {
+  const int64_t total = int64_t(T) * H * W;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int x = int(i % W);
+    int64_t r = i / W;
+    const int y = int(r % H);
+    const int t = int(r / H);
+    const double* c = cam + int64_t(t) * 16;
+    double d = disp_f64 ? reinterpret_cast<const double*>(disp)[i] : double(reinterpret_cast<const float*>(disp)[i]);
+    d = fmin(fmax(d, 1e-8), 1e8);
+    const double depth = __ddiv_rn(1.0, d);
+    const double px = double(float(x) + 0.5f), py = double(float(y) + 0.5f);       // float32 pixel centres like the ref
+    const double cx = __dmul_rn(__dadd_rn(__dmul_rn(c[0], px), c[1]), depth);
+    const double cy = __dmul_rn(__dadd_rn(__dmul_rn(c[2], py), c[3]), depth);
+    const double cz = depth;
+    double* o = out + i * 3;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double* p = c + 4 + 4 * k;
+      o[k] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(p[0], cx), __dmul_rn(p[1], cy)), __dmul_rn(p[2], cz)), p[3]);
+    }
+  }
+}
+
 static unsigned igrid(int64_t n) {
   int64_t g = ceil_div(n, 256);
   const int64_t cap = int64_t(num_sms()) * 16;
@@ -104,6 +133,14 @@ int aether_resize_bilinear_u8(const void* src, void* dst, int32_t T, int32_t h, 
   const double sy = 1.0 / (double(H) / double(h)), sx = 1.0 / (double(W) / double(w));
   resize_bilinear_u8_kernel<<<igrid(int64_t(T) * H * W), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const uint8_t*>(src), reinterpret_cast<uint8_t*>(dst), T, h, w, H, W, sy, sx);
+  return cudaGetLastError() == cudaSuccess ? AETHER_OK : AETHER_ERR_CUDA;
+}
+
+int aether_project_points(const void* disparity, int32_t disparity_is_f64, const double* cam, double* points, int32_t T,
+                          int32_t H, int32_t W, void* stream) {
+  if (!disparity || !cam || !points || T <= 0 || H <= 0 || W <= 0) return AETHER_ERR_INVALID;
+  project_points_kernel<<<igrid(int64_t(T) * H * W), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      disparity, disparity_is_f64, cam, points, T, H, W);
   return cudaGetLastError() == cudaSuccess ? AETHER_OK : AETHER_ERR_CUDA;
 }
 

@@ -336,6 +336,11 @@ int aether_disparity_to_depth(double* dst, int64_t dst_s0, int64_t dst_s1, const
  * aether_u8_frames_to_model_input: dst bf16 [F, 3, H, W] = 2 * (src / 255) - 1 of a uint8 crop src[F, H, W, 3] (element
  *   strides stride_t, stride_h; pixels contiguous): `/ 255.0`, the centre crop at the target size, the layout change,
  *   the [-1, 1] map and the bf16 cast of pipeline :451-512 in one pass. */
+/* points[T, H, W, 3] (fp64) = camera-to-world un-projection of depth = 1 / clip(disparity, 1e-8, 1e8) (disparity fp32 or
+ * fp64 [T, H, W]); cam[t] = {1/f, -cx/f, 1/f, -cy/f, pose rows 0..2 (3 x 4, row-major)} as 16 doubles.  `project` of
+ * aether/utils/postprocess_utils.py:381-403 for every frame of scripts/demo.py:404-420. */
+int aether_project_points(const void* disparity, int32_t disparity_is_f64, const double* cam, double* points, int32_t T,
+                          int32_t H, int32_t W, void* stream);
 int aether_resize_bilinear_u8(const void* src, void* dst, int32_t T, int32_t h, int32_t w, int32_t H, int32_t W,
                               void* stream);
 int aether_u8_frames_to_model_input(const void* src, int64_t stride_t, int64_t stride_h, void* dst, int32_t F, int32_t H,

@@ -34,6 +34,42 @@ def _mod(name):
     return m
 
 
+class _AutoStub(types.ModuleType):
+    """A module whose every attribute is a stub object (callable, subclassable, attribute-chainable)."""
+
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        v = type(name, (), {"__init__": lambda self, *a, **k: None, "__call__": lambda self, *a, **k: None})
+        setattr(self, name, v)
+        return v
+
+
+def _install_autostubs(roots):
+    import importlib.abc
+    import importlib.machinery
+
+    class Finder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+        def find_spec(self, fullname, path=None, target=None):
+            if fullname.split(".")[0] in roots and fullname not in sys.modules:
+                return importlib.machinery.ModuleSpec(fullname, self, is_package=True)
+            return None
+
+        def create_module(self, spec):
+            m = _AutoStub(spec.name)
+            m.__path__ = []
+            return m
+
+        def exec_module(self, module):
+            pass
+
+    for r in roots:             # drop the minimal stand-ins registered earlier for these roots' submodules
+        for k in [k for k in sys.modules if k == r or k.startswith(r + ".")]:
+            if not isinstance(sys.modules[k], _AutoStub) and k not in ("matplotlib", "imageio", "imageio.v3"):
+                pass
+    sys.meta_path.append(Finder())
+
+
 def install():
     if "aether_reference_shim_installed" in sys.modules:
         return
@@ -147,13 +183,24 @@ def install():
     acc.Accelerator = type("Accelerator", (), {"__init__": lambda self, **kw: None})
     acc.PartialState = type("PartialState", (), {})
     im = _mod("imageio")
+    im.__path__ = []                     # a package: imageio.v2 etc. resolve through the auto-stub finder below
     im.v3 = _mod("imageio.v3")
     ru = _mod("rootutils")
     ru.setup_root = lambda *a, **k: None
     mpl = _mod("matplotlib")
+    mpl.__path__ = []
     mpl.colormaps = {}
     pf = _mod("plyfile")
     pf.PlyData = pf.PlyElement = object
+    # filterpy: a real (restated) Kalman filter, the smoothing code computes with it (oracle/kalman.py)
+    from oracle.kalman import KalmanFilter as _OracleKalman
+    fp = _mod("filterpy")
+    fpk = _mod("filterpy.kalman")
+    fpk.KalmanFilter = _OracleKalman
+    fp.kalman = fpk
+    # everything else the launcher / demo scripts import at module level but never touch on the paths we execute
+    # (evo.*, trimesh, gradio, matplotlib.*, imageio.v2, tqdm is real): import-anything stand-ins
+    _install_autostubs(("evo", "trimesh", "gradio", "matplotlib", "imageio", "viser", "moviepy"))
     if str(REFERENCE_ROOT) not in sys.path:
         sys.path.insert(0, str(REFERENCE_ROOT))
     sys.modules["aether_reference_shim_installed"] = types.ModuleType("aether_reference_shim_installed")
@@ -185,3 +232,15 @@ def reference_depth_tools_module():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod
+
+
+def reference_rel_pose_module():
+    install()
+    import evaluation.rel_pose.launch_aether as EVP
+    return EVP
+
+
+def reference_demo_module():
+    install()
+    import scripts.demo as DEMO
+    return DEMO

@@ -242,11 +242,100 @@ def make_depth_eval():
     print("depth_eval.npz", {k: out[f"{k}__vals"][:2] for k in DEPTH_EVAL_MODES})
 
 
+def _stats(a):
+    a = np.asarray(a, dtype=np.float64)
+    return np.array([a.sum(), np.abs(a).sum(), (a * a).sum()])
+
+
+def make_pose_blend():
+    """aether/utils/postprocess_utils.py (raymap_to_poses, postprocess_pointmap, smoothing, alignment, SLERP), the rel-pose
+    window blend (evaluation/rel_pose/launch_aether.py:124-250) and the demo merge (scripts/demo.py:235-422), all executed
+    from the reference's files on the deterministic inputs of tests/helpers.py (filterpy = oracle/kalman.py stand-in)."""
+    from types import SimpleNamespace
+    from helpers import fake_pose_window, raymap_from_poses, synthetic_trajectory
+    POST = shim.reference_postprocess_module()
+    EVP = shim.reference_rel_pose_module()
+    DEMO = shim.reference_demo_module()
+    out = {}
+    # -- raymap -> poses / fov, point map
+    traj = synthetic_trajectory(17, seed=3)
+    ray = raymap_from_poses(traj, 12, 20, focal_px=150.0, scale=1.0)
+    pose, fx, fy = POST.raymap_to_poses(ray.copy())
+    out["r2p__pose"], out["r2p__fovx"], out["r2p__fovy"] = pose, fx, fy
+    _, disp, _ = fake_pose_window(0, 17, h=12, w=20, seed=1)
+    for mode in ("none", "simple", "kalman"):
+        pcd = POST.postprocess_pointmap(disp.copy(), ray.copy(), smooth_camera=(mode != "none"), smooth_method=mode)
+        out[f"pcd_{mode}__pose"] = pcd["camera_pose"]
+        out[f"pcd_{mode}__K"] = pcd["intrinsics"]
+        out[f"pcd_{mode}__points"] = _stats(pcd["pointmap"])
+        out[f"pcd_{mode}__points_sub"] = subsample(pcd["pointmap"], (4, 16, 16, 1))
+    # -- smoothing / alignment / interpolation primitives
+    noisy = synthetic_trajectory(41, seed=5)
+    out["smooth_gaussian"] = POST.smooth_poses(noisy.copy(), 5, "gaussian")
+    out["smooth_savgol"] = POST.smooth_poses(noisy.copy(), 7, "savgol")
+    out["smooth_kalman"] = POST.smooth_trajectory(noisy.copy(), 5)
+    static = np.repeat(noisy[:1], 12, axis=0) + 1e-4 * np.random.default_rng(0).standard_normal((12, 4, 4)) * (np.arange(16).reshape(4, 4) % 4 == 3)
+    st = POST.detect_static_sequence(static)
+    out["static__flags"] = np.array([float(st[0]), st[1], st[2]])
+    out["static__smoothed"] = POST.adaptive_pose_smoothing(static.copy(), st[1], st[2])
+    a, b = synthetic_trajectory(33, seed=7)[:, :3, :4], synthetic_trajectory(33, seed=8)[:, :3, :4]
+    R, T, sc = POST.align_camera_extrinsics(torch.from_numpy(a), torch.from_numpy(b))
+    out["align__R"], out["align__T"], out["align__s"] = R.numpy(), T.numpy(), np.float64(sc)
+    out["align__applied"] = POST.apply_transformation(torch.from_numpy(a), R, T, sc).numpy()
+    out["interp"] = np.stack([POST.interpolate_poses(noisy[3], noisy[30], wgt) for wgt in (0.0, 0.25, 0.5, 1.0)])
+    out["interp_close"] = POST.interpolate_poses(noisy[3], noisy[4], 0.3)
+    # -- rank 1: rel-pose windows (105 frames -> starts 0, 32, 64), fake pipeline
+    class FakePipe:
+        def __call__(self, video, num_inference_steps, num_frames, generator, return_dict, fps):
+            t0 = int(video[0, 0, 0, 0])
+            rgb, d, r = fake_pose_window(t0, num_frames, seed=2)
+            return rgb[None], d[None], r[None]
+    frames = np.zeros((1, 105, 24, 40, 3))
+    frames[0, :, 0, 0, 0] = np.arange(105)                  # the fake pipeline reads the window start from the clip
+    orig = torch.Generator
+
+    class _Gen:
+        def __init__(self, device=None):
+            pass
+
+        def manual_seed(self, s):
+            return self
+    torch.Generator = _Gen
+    try:
+        res = EVP.process_video_with_sliding_window(FakePipe(), frames, 4, 42)
+    finally:
+        torch.Generator = orig
+    for k in ("rgb", "disparity", "focals"):
+        out[f"relpose__{k}"] = _stats(res[k])
+    out["relpose__poses"] = res["poses"]
+    out["relpose__range"] = np.array(res["range"])
+    out["relpose__disparity_sub"] = subsample(res["disparity"], (5, 4, 4))
+    # -- rank 2: demo merge (89 frames, windows of 41, stride 24 -> starts 0, 24, 48)
+    starts = DEMO.get_window_starts(89, 41, 24)
+    out["demo__starts"] = np.array(starts)
+    for align in (False, True):
+        wins = []
+        for t0 in starts:
+            rgb, d, r = fake_pose_window(t0, 41, seed=4)
+            wins.append(SimpleNamespace(rgb=rgb, disparity=d, raymap=r))
+        args = SimpleNamespace(width=40, height=24, smooth_camera=True, smooth_method="kalman", align_pointmaps=align)
+        m_rgb, m_disp, m_pose, pts = DEMO.blend_and_merge_window_results(wins, starts, args)
+        tag = f"demo_align{int(align)}"
+        out[f"{tag}__rgb"], out[f"{tag}__disp"], out[f"{tag}__pts"] = _stats(m_rgb), _stats(m_disp), _stats(pts)
+        out[f"{tag}__poses"] = m_pose
+        out[f"{tag}__pts_sub"] = subsample(np.asarray(pts), (6, 4, 4, 1))
+        out[f"{tag}__disp_sub"] = subsample(m_disp, (6, 4, 4))
+    np.savez_compressed(HERE / "pose_blend.npz", **out)
+    print("pose_blend.npz", len(out), "arrays; relpose range", out["relpose__range"], "demo starts", starts)
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
-    which = sys.argv[1:] or ["rope", "scale", "sliding", "pipeline", "prepare", "depth_eval"]
+    which = sys.argv[1:] or ["rope", "scale", "sliding", "pipeline", "prepare", "depth_eval", "pose_blend"]
     if "depth_eval" in which:
         make_depth_eval()
+    if "pose_blend" in which:
+        make_pose_blend()
     if "prepare" in which:
         make_prepare_input()
     if "rope" in which:

@@ -151,3 +151,62 @@ def depth_eval_case(seed=0, frames=3, h=48, w=64):
     pred = np.abs(pred) + 0.05
     mask = g.random(gt.shape) > 0.2
     return pred.astype(np.float64), gt.astype(np.float64), mask
+
+
+# ------------------------------------------------------------------------------------------------------
+# synthetic camera trajectory / raymap / window outputs for the pose and point-map goldens (8f ranks 1, 2)
+# ------------------------------------------------------------------------------------------------------
+def _rot_xyz(ax, ay, az):
+    cx, sx, cy, sy, cz, sz = np.cos(ax), np.sin(ax), np.cos(ay), np.sin(ay), np.cos(az), np.sin(az)
+    rx = np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]])
+    ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+    rz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]])
+    return rz @ ry @ rx
+
+
+def synthetic_trajectory(n, seed=0):
+    """camera-to-world poses [n, 4, 4]: a smooth arc with a slow pan plus a little jitter."""
+    g = np.random.default_rng(seed)
+    t = np.linspace(0, 1, n)
+    poses = np.zeros((n, 4, 4))
+    for i, ti in enumerate(t):
+        poses[i, :3, :3] = _rot_xyz(0.05 * np.sin(3 * ti), 0.6 * ti, 0.03 * np.cos(2 * ti))
+        poses[i, :3, 3] = [0.8 * np.sin(1.5 * ti), 0.05 * ti, 1.2 * ti]
+        poses[i, 3, 3] = 1.0
+    poses[:, :3, 3] += 0.004 * g.standard_normal((n, 3))
+    return poses
+
+
+def raymap_from_poses(poses, h, w, focal_px, scale=1.0):
+    """float32 raymap [n, 6, h, w] the way the model emits it: channels 0:3 ray directions through the pixel centres of an
+    (8h x 8w) image with focal length `focal_px`, 3:6 sign(o) * log1p(|o|) of the (scaled) camera centre."""
+    n = poses.shape[0]
+    H, W = 8 * h, 8 * w
+    ys, xs = np.meshgrid((np.arange(h) + 0.5) * 8, (np.arange(w) + 0.5) * 8, indexing="ij")
+    d_cam = np.stack([(xs - W / 2) / focal_px, (ys - H / 2) / focal_px, np.ones_like(xs)], axis=0)      # [3, h, w]
+    out = np.zeros((n, 6, h, w), dtype=np.float32)
+    for i in range(n):
+        out[i, :3] = np.einsum("ij,jhw->ihw", poses[i, :3, :3], d_cam)
+        o = poses[i, :3, 3] * scale
+        out[i, 3:] = (np.sign(o) * np.log1p(np.abs(o)))[:, None, None]
+    return out
+
+
+def fake_pose_window(t_start, frames, h=3, w=5, seed=0, total=160):
+    """One window's pipeline outputs (rgb f32 [F, 8h, 8w, 3], disparity f32 [F, 8h, 8w], raymap f32 [F, 6, h, w]) cut out
+    of a global synthetic scene, with a window-dependent similarity (scale + small rotation) and noise on the camera, and a
+    window-dependent gain on the disparity -- what the alignment code has to undo."""
+    g = np.random.default_rng(seed * 1000 + t_start)
+    H, W = 8 * h, 8 * w
+    traj = synthetic_trajectory(total, seed)[t_start:t_start + frames].copy()
+    s = 1.0 + 0.15 * ((t_start // 8) % 3)
+    Rw = _rot_xyz(0.02 * (t_start % 5), -0.03 * (t_start % 3), 0.01)
+    traj[:, :3, :3] = traj[:, :3, :3] @ Rw
+    traj[:, :3, 3] = s * traj[:, :3, 3] + 0.002 * g.standard_normal((frames, 3))
+    ray = raymap_from_poses(traj, h, w, focal_px=0.9 * W, scale=10.0)
+    yy, xx = np.meshgrid(np.linspace(0, 1, H), np.linspace(0, 1, W), indexing="ij")
+    f = (np.arange(frames) + t_start)[:, None, None]
+    disp = (0.25 + 0.5 * xx[None] * (0.6 + 0.4 * np.sin(0.11 * f)) + 0.2 * yy[None]) * (0.8 + 0.1 * ((t_start // 8) % 4))
+    disp = np.clip(disp + 0.01 * g.standard_normal(disp.shape), 0.02, 1.0)
+    rgb = np.clip(np.stack([xx[None] + 0 * f, yy[None] + 0 * f, 0.5 + 0.5 * np.sin(0.2 * f) + 0 * xx[None]], axis=-1), 0, 1)
+    return rgb.astype(np.float32), disp.astype(np.float32), ray.astype(np.float32)
