@@ -85,7 +85,7 @@ def timestep_sinusoid(timesteps: torch.Tensor, dim: int, flip_sin_to_cos: bool, 
     bit differs between hosts, and a 1-ulp change of a frequency moves the angle of t = 999 by 6e-5 -- enough to make
     goldens generated from this oracle host-dependent (observed: MKL AVX2 vs AVX-512 paths)."""
     half = dim // 2
-    exponent = -math.log(max_period) * torch.arange(half, dtype=torch.float32)
+    exponent = -math.log(max_period) * torch.arange(half, dtype=torch.float32, device=timesteps.device)
     exponent = exponent / (half - shift)
     freq = torch.exp(exponent.double()).float()
     emb = timesteps[:, None].float() * freq[None, :]
