@@ -67,18 +67,20 @@ def test_committed_bench_lines_follow_the_contract():
     """The bench lines committed under profiles/ (written by bench.py on a B200) carry every key of the measurement
     contract, with consistent values."""
     import json
-    line = json.loads((ROOT / "profiles" / "r1_bench_1gpu_default.json").read_text())
+    line = json.loads((ROOT / "profiles" / "r2_bench_1gpu_k3.json").read_text())
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
-              "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+              "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline",
+              "collective_ms", "blend_ms", "config5_4step", "exchange_blend_check", "gpu_library_baseline"):
         assert k in line, k
-    assert line["n_gpus"] == 1 and line["steps"] == 50 and line["warmup"] >= 3 and line["higher_is_better"] is True
+    assert line["n_gpus"] == 1 and line["warmup"] >= 3 and line["higher_is_better"] is True
     assert line["scaling"] == "weak" and line["dtype"] == "bf16" and line["data"] == "synthetic"
-    assert "workload" in line["config"] and "l2" in line["config"]
-    # value = latent frames of one 50-step generation / its time
-    assert line["value"] == pytest.approx(11 / (50 * line["ms_per_step"] / 1000.0), rel=1e-6)
+    assert "workload" in line["config"] and "l2" in line["config"] and line["config"]["denoise_steps"] == 50
+    assert "INVALID_FOR_HEADLINE" not in line["config"]
+    # a step is one round = one 11-latent-frame generation per rank
+    assert line["value"] == pytest.approx(line["n_gpus"] * 11 / (line["ms_per_step"] / 1000.0), rel=1e-6)
     e2e = line["e2e"]
-    assert e2e["unit"] == line["unit"] and e2e["h2d_bytes_per_step"] > 0 and e2e["d2h_bytes_per_step"] > 0
-    assert 0 < e2e["value"] < line["value"]                       # copies and the VAE are inside the e2e region
+    assert e2e["unit"] == line["unit"] and e2e["h2d_bytes_per_step"] == 41 * 480 * 720 * 3 and e2e["d2h_bytes_per_step"] > 0
+    assert 0 < e2e["value"] <= line["value"] * 1.01                # host copies are inside the e2e region
     rf = line["roofline"]
     assert rf["bound"] in ("hbm", "tensor") and rf["unit"] in ("GB/s", "TFLOP/s")
     assert rf["frac"] == pytest.approx(rf["achieved"] / rf["peak"], rel=1e-9) and rf["traffic"] > 0
@@ -86,8 +88,12 @@ def test_committed_bench_lines_follow_the_contract():
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] > 0 and cb["sample"]
     assert line["gpu_launches"] > 0 and line["clocks"]["sm_mhz"] > 0
     assert not set(line["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
-    ref = json.loads((ROOT / "profiles" / "r1_bench_reference_arm.json").read_text())
+    assert line["exchange_blend_check"]["matches_rtol_2e-6"] is True
+    lib = line["gpu_library_baseline"]
+    assert lib["ours_dit_forward_ms"] < lib["dit_forward_ms"]
+    ref = json.loads((ROOT / "profiles" / "r2_bench_reference_arm.json").read_text())
     assert ref["impl"] == "reference" and ref["metric"] == line["metric"] and ref["unit"] == line["unit"]
+    assert ref["config"]["workload"] == line["config"]["workload"]
     assert ref["e2e"]["h2d_bytes_per_step"] == 0 and ref["cpu_baseline"]["value"] == ref["value"]
 
 
