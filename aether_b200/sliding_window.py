@@ -393,11 +393,12 @@ class TileParallelRun:
             self._marks = []
             self.stats.clear()
 
-    def fetch_finalized(self, out: Optional[torch.Tensor] = None):
+    def fetch_finalized(self, out: Optional[torch.Tensor] = None, discard: bool = False):
         """Blend rank, multi-window clips: the frames of the blended disparity that no later window can touch any more
         (everything before the start of the next window to be pushed), copied to the host since the previous call --
         lets a caller stream results out while later tiles are still being computed.  Returns (first_frame, numpy
-        fp64 [n, H, W]) or None when nothing new is final.  `out`: optional pinned host tensor to stage through."""
+        fp64 [n, H, W]) or None when nothing new is final.  `out`: optional pinned host tensor to stage through (used when
+        it is large enough); `discard`: only advance the "already fetched" mark, copy nothing."""
         if self.blend is None or self.blend.final is None:
             return None
         m = self.blend.windows_done
@@ -405,8 +406,10 @@ class TileParallelRun:
         if m == 0 or upto <= self._fetched:
             return None
         lo, self._fetched = self._fetched, upto
+        if discard:
+            return None
         src = self.blend.final[lo:upto]
-        if out is not None:
+        if out is not None and out.shape[0] >= upto - lo:
             dst = out[: upto - lo]
             dst.copy_(src, non_blocking=True)
             torch.cuda.current_stream(self.device).synchronize()
