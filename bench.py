@@ -64,6 +64,27 @@ WORKLOAD = ("sliding-window evaluation rounds (configs[4] geometry: 480x853 clip
             "blend chain advance")
 
 
+def bench_config(world: int, tile_steps: int, steps: int, warmup: int, attention_mode: int = 5) -> dict:
+    """The `config` object of the JSON line -- identical for the product arm and the `--impl reference` arm."""
+    n_e2e = 1 + ((warmup + steps + 1) * world) % 2
+    cfg = {"workload": WORKLOAD,
+           "model": "AetherV1 DiT geometry (42 layers, 48x64, in 96 / out 56) + CogVideoX-5b VAE geometry, seeded synthetic "
+                    "weights",
+           "denoise_steps": tile_steps, "tokens": S_TOKENS, "attention_mode": attention_mode, "tiles_per_round": world,
+           "clip_frames": clip_frames_for_tiles((warmup + steps + n_e2e) * world),
+           "parallelism": f"tile-parallel x{world}: round-robin tiles, NCCL p2p of the disparity tiles to the blend rank "
+                          f"each round, streaming blend chain on rank 0",
+           "l2": "per-step working set (11.1 GB weights + ~1.4 GB activations) >> 126 MB L2; no explicit flush"}
+    if tile_steps != DENOISE_STEPS:
+        cfg["INVALID_FOR_HEADLINE"] = f"--tile-steps {tile_steps} (development run; the metric needs 50)"
+    return cfg
+
+
+def clip_frames_for_tiles(n_tiles: int) -> int:
+    n_windows = (n_tiles + 1) // 2
+    return WINDOW + STRIDE_T * (n_windows - 1)
+
+
 def _peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -179,8 +200,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "latent-frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "device": "host CPU", "samples_timed": len(r["samples_s"]),
-                       "extrapolated": True},
+            "config": bench_config(args.gpus, args.tile_steps, args.steps, max(args.warmup, 3),
+                                   int(os.environ.get("AETHER_ATTENTION_MODE", "5"))),
+            "reference_detail": {"device": "host CPU", "samples_timed": len(r["samples_s"]), "extrapolated": True},
             "cpu_baseline": cpu_baseline_dict(r),
             "e2e": {"value": r["value"], "unit": "latent-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -214,11 +236,6 @@ class SyntheticClip:
             g = torch.Generator(device=self.device).manual_seed(seed)
             self._cache[key] = torch.rand((n, hh, ww, 3), device=self.device, generator=g, dtype=torch.float32)
         return self._cache[key]
-
-
-def clip_frames_for_tiles(n_tiles: int) -> int:
-    n_windows = (n_tiles + 1) // 2
-    return WINDOW + STRIDE_T * (n_windows - 1)
 
 
 def gpu_library_forward_ms(dev, reps: int = 3):
@@ -444,14 +461,7 @@ def run_product(args):
             "metric": METRIC, "value": value, "unit": "latent-frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD,
-                       "model": "AetherV1 DiT geometry (42 layers, 48x64, in 96 / out 56) + CogVideoX-5b VAE geometry, "
-                                "seeded synthetic weights",
-                       "denoise_steps": tile_steps, "tokens": S_TOKENS, "attention_mode": int(model.attention_fp16_pv),
-                       "tiles_per_round": world, "clip_frames": clip.shape[1],
-                       "parallelism": f"tile-parallel x{world}: round-robin tiles, NCCL p2p of the disparity tiles to the "
-                                      f"blend rank each round, streaming blend chain on rank 0",
-                       "l2": "per-step working set (11.1 GB weights + ~1.4 GB activations) >> 126 MB L2; no explicit flush"},
+            "config": bench_config(world, tile_steps, args.steps, warmup, int(model.attention_fp16_pv)),
             "e2e": e2e,
             "collective_ms": per_round("collective_ms"), "blend_ms": per_round("blend_ms"),
             "tile_ms": per_round("tile_ms"),
@@ -464,8 +474,6 @@ def run_product(args):
                          "peak_source": peak_src, "launches_timed": attn_n, "avg_launch_ms": avg_ms,
                          "share_of_step": (avg_ms * LAYERS * tile_steps / ms_per_step) if attn_n else None},
         }
-        if tile_steps != DENOISE_STEPS:
-            line["config"]["INVALID_FOR_HEADLINE"] = f"--tile-steps {tile_steps} (development run; the metric needs 50)"
         if strong is not None:
             line["config5_4step"] = strong
         if xcheck is not None:

@@ -190,3 +190,49 @@ def test_exchange_rounds_gloo_world2(n_tiles):
         assert p.exitcode == 0
     assert all(ok for _, ok, _ in res)
     assert sum(n for _, _, n in res) == n_tiles
+
+
+def _pose_worker(rank, world, port, q):
+    """rel-pose windows dealt over 2 ranks (gloo): the blend rank must reproduce the single-process result exactly."""
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, str(ROOT))
+    sys.path.insert(0, str(ROOT / "tests"))
+    from helpers import fake_pose_window
+    from aether_b200 import pose_blend as P
+    frames = np.zeros((1, 105, 24, 40, 3))
+    frames[0, :, 0, 0, 0] = np.arange(105)
+    ran = []
+
+    def window_fn(clip):
+        ran.append(int(clip[0, 0, 0, 0]))
+        return fake_pose_window(ran[-1], clip.shape[0], seed=2)
+    res = P.process_video_with_sliding_window(None, frames, 4, 42, rank=rank, world_size=world, window_fn=window_fn)
+    ok = True
+    if rank == 0:
+        single = P.process_video_with_sliding_window(None, frames, 4, 42, window_fn=lambda c: fake_pose_window(
+            int(c[0, 0, 0, 0]), c.shape[0], seed=2))
+        ok = all(np.array_equal(res[k], single[k]) for k in ("rgb", "disparity", "poses", "focals"))
+        ok = ok and ran[:2] == [0, 64]                      # windows 0 and 2 ran here, window 1 on the other rank
+    else:
+        ok = res is None and ran == [32]
+    q.put((rank, ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_rel_pose_windows_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_pose_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in res), res
