@@ -42,6 +42,14 @@ struct Params {
 // Round-1 variants of this kernel (per-warp pipelined softmax, 12.5-37.5 % of the exponentials on the FMA pipe,
 // interleaved consumers, a split schedule for the ragged rows) measured equal or slower and live on, unbuilt, under
 // tools/experiments/attention/ together with the 16-softmax-warp, 1-tile-per-CTA, 64-key-tile and 3-query-tile kernels.
+// Round 2: the scale (s * sl2 - m) and row-sum math run on fma.rn.f32x2 / add.rn.f32x2, two elements per issue slot
+// (SASS per 128-key tile and row: 128 MUFU.EX2, 64 FFMA2, 64 FADD2, 64 FMNMX3, 64 F2FP instead of 128 FFMA + 128 FADD):
+// 3.317 -> 3.159 ms isolated, 3.850 -> 3.752 ms inside the power-capped step.  Tried and dropped in the same experiment
+// (profiles/r2_attn_experiments_lazy_packed.log): starting the exponentials of tile j with the stale offset of tile j-1
+// and taking the tile maximum off the critical path ("lazy max", with a redo from registers for pathological jumps) --
+// 3.93 ms alone, 3.70 ms combined with the packed math: S has to stay live in registers next to P; and, on top of the
+// packed math, 12.5 % / 25 % of the exponentials as the FMA-pipe polynomial (profiles/r2_attn_experiments_packed_poly.log):
+// 3.165 / 3.126 ms isolated against 3.160, no difference inside the power-capped step.
 __global__ void __launch_bounds__(THREADS, 1)
 attention_v3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -276,6 +284,7 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Params p
         for (int c = 0; c < 128; ++c)
           if (c >= kv_valid) s[c] = 0xFF800000u;
       }
+      // row maximum of the tile (3-input max tree), needed before the first exponential
       float mx[8];
 #pragma unroll
       for (int c = 0; c < 8; ++c) mx[c] = __uint_as_float(s[c]);
@@ -283,48 +292,61 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const Params p
       for (int c = 8; c < 128; ++c) mx[c & 7] = fmaxf(mx[c & 7], __uint_as_float(s[c]));
       const float m_tile =
           fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])));
-      const float m_new = fmaxf(m_used, m_tile);
-      const bool need = (m_new - m_used) > rescale_thresh;
       bool pv_prev_done = (j == 0);
-      if (__any_sync(0xffffffffu, need)) {
-        const float alpha = fast_exp2((m_used - m_new) * sl2);
-        l *= alpha;
-        m_used = m_new;
-        if (j > 0) {
-          mbar_wait(&p_free[t], (j - 1) & 1);      // PV_t(j-1) retired: O_t is quiescent
-          pv_prev_done = true;
-          tc_fence_after();
-          uint32_t o0[32], o1[32];
-          tmem_ld_32x32b_x32(o_addr, o0);
-          tmem_ld_32x32b_x32(o_addr + 32, o1);
-          tc_wait_ld();
+      auto scale_O = [&](float alpha) {            // O_t *= alpha (O_t must be quiescent: PV_t(j-1) retired)
+        uint32_t o0[32], o1[32];
+        tmem_ld_32x32b_x32(o_addr, o0);
+        tmem_ld_32x32b_x32(o_addr + 32, o1);
+        tc_wait_ld();
 #pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            o0[c] = __float_as_uint(__uint_as_float(o0[c]) * alpha);
-            o1[c] = __float_as_uint(__uint_as_float(o1[c]) * alpha);
+        for (int c = 0; c < 32; ++c) {
+          o0[c] = __float_as_uint(__uint_as_float(o0[c]) * alpha);
+          o1[c] = __float_as_uint(__uint_as_float(o1[c]) * alpha);
+        }
+        tmem_st_32x32b_x32(o_addr, o0);
+        tmem_st_32x32b_x32(o_addr + 32, o1);
+      };
+      auto wait_pv_prev = [&]() {
+        if (!pv_prev_done) {
+          mbar_wait(&p_free[t], (j - 1) & 1);      // PV_t(j-1) retired: O_t quiescent, P_t writable
+          tc_fence_after();
+          pv_prev_done = true;
+        }
+      };
+      {
+        const float m_new = fmaxf(m_used, m_tile);
+        const bool need = (m_new - m_used) > rescale_thresh;
+        if (__any_sync(0xffffffffu, need)) {       // lazy rescale: only when some row's maximum grew by more than 2^8
+          const float alpha = fast_exp2((m_used - m_new) * sl2);
+          l *= alpha;
+          m_used = m_new;
+          if (j > 0) {
+            wait_pv_prev();
+            scale_O(alpha);
           }
-          tmem_st_32x32b_x32(o_addr, o0);
-          tmem_st_32x32b_x32(o_addr + 32, o1);
         }
       }
       const float neg_m = -m_used * sl2;
-      float sum[8];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) sum[c] = 0.f;
       uint32_t pk[64];
+      // P = 2^(s * sl2 + neg_m) packed to bf16, row sum in fp32 -- packed f32x2 math (pairs of adjacent keys)
+      const uint64_t sl2x2 = pack_f32x2(sl2, sl2), negx2 = pack_f32x2(neg_m, neg_m);
+      uint64_t acc[4] = {0ull, 0ull, 0ull, 0ull};               // four (0.0f, 0.0f) accumulator pairs
 #pragma unroll
       for (int c = 0; c < 128; c += 2) {
-        const float p0 = fast_exp2(fmaf(__uint_as_float(s[c]), sl2, neg_m));
-        const float p1 = fast_exp2(fmaf(__uint_as_float(s[c + 1]), sl2, neg_m));
-        sum[c & 7] += p0;
-        sum[(c + 1) & 7] += p1;
+        float x0, x1;
+        unpack_f32x2(ffma2(pack_f32x2(__uint_as_float(s[c]), __uint_as_float(s[c + 1])), sl2x2, negx2), x0, x1);
+        const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
+        acc[(c >> 1) & 3] = fadd2(acc[(c >> 1) & 3], pack_f32x2(p0, p1));
         pk[c >> 1] = pack_bf16x2(p0, p1);
       }
-      l += ((sum[0] + sum[1]) + (sum[2] + sum[3])) + ((sum[4] + sum[5]) + (sum[6] + sum[7]));
-      if (!pv_prev_done) {                         // P_t is still being read by PV_t(j-1) until p_free flips
-        mbar_wait(&p_free[t], (j - 1) & 1);
-        tc_fence_after();
+      float tile_sum;
+      {
+        float a0, a1;
+        unpack_f32x2(fadd2(fadd2(acc[0], acc[1]), fadd2(acc[2], acc[3])), a0, a1);
+        tile_sum = a0 + a1;
       }
+      l += tile_sum;
+      wait_pv_prev();                              // P_t is still being read by PV_t(j-1) until p_free flips
       {
         const uint32_t(&p0)[32] = *reinterpret_cast<const uint32_t(*)[32]>(&pk[0]);
         const uint32_t(&p1)[32] = *reinterpret_cast<const uint32_t(*)[32]>(&pk[32]);
@@ -441,6 +463,7 @@ int attention_v3_launch(const CUtensorMap& tm, int B, int S, int H, void* out, f
                         int64_t workspace_bytes, cudaStream_t stream) {
   static SmemGrant grant;
   AETHER_CUDA_OK(ensure_dynamic_smem(grant, attn3::attention_v3_kernel, attn3::SMEM_BYTES));
+  const auto kern = attn3::attention_v3_kernel;
   attn3::Params p;
   p.B = B; p.H = H; p.S = S;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
@@ -455,12 +478,12 @@ int attention_v3_launch(const CUtensorMap& tm, int B, int S, int H, void* out, f
   if (splits > n_kv) splits = n_kv;
   const int64_t need = int64_t(rem) * splits * 2 * attn3::BQ * (attn3::DH + 2) * 4 + 256;
   if (splits < 2 || workspace == nullptr || workspace_bytes < need) {
-    attn3::attention_v3_kernel<<<(unsigned)items, attn3::THREADS, attn3::SMEM_BYTES, stream>>>(tm, p);
+    kern<<<(unsigned)items, attn3::THREADS, attn3::SMEM_BYTES, stream>>>(tm, p);
     AETHER_CUDA_OK(cudaGetLastError());
     return AETHER_OK;
   }
   const int64_t full = items - rem;
-  attn3::attention_v3_kernel<<<(unsigned)full, attn3::THREADS, attn3::SMEM_BYTES, stream>>>(tm, p);
+  kern<<<(unsigned)full, attn3::THREADS, attn3::SMEM_BYTES, stream>>>(tm, p);
   attn3::Params q = p;
   q.item_begin = (int)full;
   q.kv_splits = splits;
@@ -471,7 +494,7 @@ int attention_v3_launch(const CUtensorMap& tm, int B, int S, int H, void* out, f
   char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
   q.part_o = reinterpret_cast<float*>(base);
   q.part_ml = q.part_o + int64_t(rem) * splits * 2 * attn3::BQ * attn3::DH;
-  attn3::attention_v3_kernel<<<(unsigned)(rem * splits), attn3::THREADS, attn3::SMEM_BYTES, stream>>>(tm, q);
+  kern<<<(unsigned)(rem * splits), attn3::THREADS, attn3::SMEM_BYTES, stream>>>(tm, q);
   const int warps = rem * 2 * attn3::BQ;
   attn3::attention_combine_kernel<<<(unsigned)ceil_div(int64_t(warps) * 32, 256), 256, 0, stream>>>(q, rem);
   AETHER_CUDA_OK(cudaGetLastError());
