@@ -23,7 +23,7 @@ class DitConfig(C.Structure):
                 ("in_channels", c_int32), ("out_channels", c_int32), ("patch_size", c_int32),
                 ("time_embed_dim", c_int32), ("text_embed_dim", c_int32), ("flip_sin_to_cos", c_int32),
                 ("freq_shift", c_float), ("norm_eps", c_float), ("ff_mult", c_int32),
-                ("attention_fp16_pv", c_int32), ("fused_qkv_epilogue", c_int32)]
+                ("attention_fp16_pv", c_int32), ("fused_qkv_epilogue", c_int32), ("attention_split_tail", c_int32)]
 
 
 class DitLayerWeights(C.Structure):

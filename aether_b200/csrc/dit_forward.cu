@@ -86,7 +86,8 @@ Workspace carve(const AetherDitConfig& c, int B, int S, char* base) {
   ws.temb_h = reinterpret_cast<float*>(take(int64_t(B) * c.time_embed_dim * 4));
   ws.temb = reinterpret_cast<float*>(take(int64_t(B) * c.time_embed_dim * 4));
   ws.mod = reinterpret_cast<float*>(take(int64_t(B) * (12 * int64_t(c.num_layers) + 2) * D * 4));
-  ws.attn_ws_bytes = c.attention_fp16_pv == 5 ? aether::attention_v3_workspace_bytes(B, S, c.num_heads) : 0;
+  ws.attn_ws_bytes = (c.attention_fp16_pv == 5 && c.attention_split_tail != 0)
+                         ? aether::attention_v3_workspace_bytes(B, S, c.num_heads) : 0;
   ws.attn_ws = take(ws.attn_ws_bytes);
   ws.total = off;
   return ws;

@@ -137,6 +137,9 @@ class AetherTransformer3D(nn.Module):
         # QK-LayerNorm + RoPE inside the QKV GEMM epilogue (one launch less per layer; measured slower: off).  Read here,
         # once per module, and stored in the handle's config -- the C library itself never reads the environment.
         self.fused_qkv_epilogue = os.environ.get("AETHER_FUSED_QK", "0")[:1] == "1"
+        # attention variant 5 cuts the partially filled tail wave of its grid along the keys (scratch in the workspace);
+        # off => one launch, and the output of a batch item no longer depends on the batch size (fp32 merge order)
+        self.attention_split_tail = os.environ.get("AETHER_ATTENTION_SPLIT_TAIL", "1")[:1] != "0"
 
     # ------------------------------------------------------------------ torch plumbing
     @property
@@ -290,7 +293,7 @@ class AetherTransformer3D(nn.Module):
         cfg = DitConfig(c.num_attention_heads, c.attention_head_dim, c.num_layers, c.in_channels, c.out_channels,
                         c.patch_size, c.time_embed_dim, c.text_embed_dim, int(c.flip_sin_to_cos), float(c.freq_shift),
                         float(c.norm_eps), c.ff_mult, int(self.attention_fp16_pv),
-                        int(self.fused_qkv_epilogue and c.attention_head_dim == 64))
+                        int(self.fused_qkv_epilogue and c.attention_head_dim == 64), int(self.attention_split_tail))
         h = C.c_void_p()
         check(lib.aether_dit_create(C.byref(cfg), C.byref(w), C.byref(h)), "dit_create")
         self._handle = h

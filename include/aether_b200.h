@@ -131,6 +131,9 @@ typedef struct AetherDitConfig {
                                   id 2 the QKV GEMM emits the V third as fp16 */
   int32_t fused_qkv_epilogue;  /* 1: QK-LayerNorm + RoPE run inside the QKV GEMM epilogue (one launch less per layer;
                                   measured slower, default 0).  Per handle -- the library reads no environment. */
+  int32_t attention_split_tail; /* 1 (default): reserve scratch so attention variant 5 cuts its partially filled tail wave
+                                  along the keys (aether_attention_bf16_ws); 0: single launch -- results then do not
+                                  depend on how many (batch x head x query-block) items there are */
 } AetherDitConfig;
 
 typedef struct AetherDitLayerWeights {

@@ -8,7 +8,8 @@ the CFG batch of 2 whose second item starts at row 15076 (not a tile boundary).
   * k transformer layers of `aether_dit_forward` (k = 2 at B = 1; k = 1 at B = 2) + patch embed + tail vs
     oracle.dit.OracleDiT with the same k layers (the oracle times one block in 3-15 s on the box's cores);
   * all 42 layers at B = 2 against two B = 1 forwards of the same items (batch independence: the only check of the
-    full-depth CFG batch the CPU cannot give in minutes);
+    full-depth CFG batch the CPU cannot give in minutes) -- bit-equal with the single-launch attention, bf16-noise-equal
+    with the split tail wave;
   * the real-geometry VAE (block_out_channels 128/256/256/512, 3 layers per block, 240 x 360 px / 30 x 45 latent
     tiles): encode of a 17 x 160 x 432 strip and decode of 4 x 20 x 54 latents -- two horizontally overlapping tiles
     of the real tile width with their blend, two frame batches with conv caches -- vs oracle.vae (sized so that the
@@ -89,10 +90,18 @@ def test_dit_k_layers_at_full_sequence_length_match_fp32_oracle(B, k, ts):
         assert max(rb, r_last, r_first) <= 2e-2, (b, rb, r_last, r_first)
 
 
-def test_full_depth_cfg_batch_equals_two_single_forwards():
-    """42 layers, B = 2 (prediction / planning, reference :832-875) vs the same two items run one at a time."""
+@pytest.mark.parametrize("split_tail", [False, True])
+def test_full_depth_cfg_batch_equals_two_single_forwards(split_tail):
+    """42 layers, B = 2 (prediction / planning, reference :832-875) vs the same two items run one at a time.
+    Without the attention split tail every kernel reduces over K / keys in an order that does not depend on the row's
+    position in the batch: bit-equal.  With it (product default) the rows of the last, partially filled attention wave are
+    merged from key-range partials, and WHICH rows those are depends on the item count (2832 vs 5664 items): their fp32
+    merge order differs, and 42 layers of bf16 rounding spread that like any other rounding difference (measured rel-RMS
+    1.0e-2, the size of the bf16 noise of the forward itself: a 2-layer forward is 4e-3 from the fp32 oracle)."""
     from aether_b200.transformer import AetherTransformer3D
-    model = AetherTransformer3D(device=torch.device(DEV)).init_synthetic_(0).pack(release_unpacked=True)
+    model = AetherTransformer3D(device=torch.device(DEV)).init_synthetic_(0)
+    model.attention_split_tail = split_tail
+    model.pack(release_unpacked=True)
     c = model.config
     from aether_b200.rope import prepare_rotary_positional_embeddings
     g = torch.Generator(device=DEV).manual_seed(11)
@@ -106,11 +115,13 @@ def test_full_depth_cfg_batch_equals_two_single_forwards():
     singles = torch.cat([model(x[i:i + 1], e[i:i + 1], t[i:i + 1], image_rotary_emb=(cos, sin))[0] for i in range(2)])
     assert torch.isfinite(both.float()).all()
     rel, mx = _rel(both, singles)
-    print(f"full depth B=2 vs 2 x B=1: rel-rms {rel:.3e}, max-abs {mx:.3e}, bit-equal {torch.equal(both, singles)}")
-    # every kernel reduces over K / keys in an order that does not depend on the row's position in the batch
-    assert torch.equal(both, singles)
-    # and the two items really differ (the check is not vacuous)
-    assert _rel(both[0], both[1])[0] > 0.1
+    print(f"full depth B=2 vs 2 x B=1 (split_tail={split_tail}): rel-rms {rel:.3e}, max-abs {mx:.3e}, "
+          f"bit-equal {torch.equal(both, singles)}")
+    if split_tail:
+        assert rel <= 2.5e-2, rel
+    else:
+        assert torch.equal(both, singles)
+    assert _rel(both[0], both[1])[0] > 0.1              # the two items really differ (the check is not vacuous)
     model.release()
 
 
