@@ -136,6 +136,8 @@ SIGNATURES = {
                                          c_int32, c_void_p]),
     "aether_scale_copy": (C.c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int32, c_int64, c_int64, c_double,
                                     c_void_p, c_int32, c_int64, c_int64, c_int64, c_void_p]),
+    "aether_blend_link": (C.c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int32, c_int64, c_int64, c_int64, c_int64,
+                                    c_int64, c_int32, c_int64, c_int64, c_void_p, c_void_p]),
     "aether_disparity_to_depth": (C.c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int32, c_int64, c_int64, c_int64,
                                             c_int64, c_int64, c_void_p]),
 }

@@ -248,6 +248,36 @@ int aether_scale_copy(double* dst, int64_t dst_s0, int64_t dst_s1, const void* s
                                                                             apply_scale, n0, n1, n2);
   return cudaGetLastError() == cudaSuccess ? AETHER_OK : AETHER_ERR_CUDA;
 }
+// One link of the reference's blend chain as ONE call: window `win` ([n_win along `axis`] x the other two extents, fp32
+// or fp64) is appended to the fp64 accumulation `buf` whose valid extent along `axis` ends at `prev_end`; the window
+// starts at `start` (overlap = prev_end - start):   scale = compute_scale(win[:overlap], buf[start:prev_end]);
+// buf[start:prev_end] = buf[start:prev_end] * w + scale * win[:overlap] * (1 - w);  buf[prev_end:start + n_win] = scale *
+// win[overlap:]   (launch_aether.py:193-250 spatial, :268-284 temporal).  The SURVEY 8(b) `blend_tiles` entry point: three
+// kernels on `stream`, the scale never leaves the device.  e0, e1, e2 = extents of `win`; strides in elements.
+int aether_blend_link(double* buf, int64_t buf_s0, int64_t buf_s1, const void* win, int32_t win_is_f64, int64_t win_s0,
+                      int64_t win_s1, int64_t e0, int64_t e1, int64_t e2, int32_t axis, int64_t start, int64_t prev_end,
+                      void* work, void* stream) {
+  if (!buf || !win || !work || axis < 0 || axis > 2 || e0 <= 0 || e1 <= 0 || e2 <= 0) return AETHER_ERR_INVALID;
+  const int64_t ext[3] = {e0, e1, e2};
+  const int64_t n_win = ext[axis], overlap = prev_end - start;
+  if (overlap <= 0 || overlap > n_win || start < 0) return AETHER_ERR_INVALID;
+  const int64_t bstr[3] = {buf_s0, buf_s1, 1}, wstr[3] = {win_s0, win_s1, 1};
+  const int64_t wsz = win_is_f64 ? 8 : 4;
+  double* acc = buf + start * bstr[axis];                                  // buf[start:prev_end] along `axis`
+  int64_t n[3] = {e0, e1, e2};
+  n[axis] = overlap;
+  int rc = aether_scale_reduce(win, win_is_f64, win_s0, win_s1, acc, 1, buf_s0, buf_s1, n[0], n[1], n[2], work, stream);
+  if (rc) return rc;
+  const double* sums = reinterpret_cast<const double*>(work);
+  rc = aether_blend_crossfade(acc, buf_s0, buf_s1, acc, 1, buf_s0, buf_s1, win, win_is_f64, win_s0, win_s1, 1.0, sums, n[0],
+                              n[1], n[2], axis, stream);
+  if (rc || overlap == n_win) return rc;
+  n[axis] = n_win - overlap;
+  const char* tail = reinterpret_cast<const char*>(win) + overlap * wstr[axis] * wsz;
+  return aether_scale_copy(buf + prev_end * bstr[axis], buf_s0, buf_s1, tail, win_is_f64, win_s0, win_s1, 1.0, sums, 1, n[0],
+                           n[1], n[2], stream);
+}
+
 int aether_disparity_to_depth(double* dst, int64_t dst_s0, int64_t dst_s1, const void* src, int32_t src_is_f64,
                               int64_t src_s0, int64_t src_s1, int64_t n0, int64_t n1, int64_t n2, void* stream) {
   if (!dst || !src || n0 <= 0 || n1 <= 0 || n2 <= 0) return AETHER_ERR_INVALID;

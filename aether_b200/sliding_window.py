@@ -187,15 +187,17 @@ def _axis_slices(axis: int):
     return lambda a, b: tuple(slice(a, b) if d == axis else slice(None) for d in range(3))
 
 
+@device_guard
 def _append_(buf: torch.Tensor, win: torch.Tensor, start: int, prev_end: int, axis: int, work: torch.Tensor):
     """One link of the reference's chain (:193-250 spatial / :268-284 temporal), in place on `buf`: `win` covers
-    [start, start + n) on `axis`, the accumulation so far ends at `prev_end`."""
-    sl = _axis_slices(axis)
-    overlap = prev_end - start
-    n_win = win.shape[axis]
-    scale_sums_(work, win[sl(0, overlap)], buf[sl(start, prev_end)])
-    _crossfade_(buf[sl(start, prev_end)], buf[sl(start, prev_end)], win[sl(0, overlap)], axis, sums=work)
-    _scale_copy_(buf[sl(prev_end, start + n_win)], win[sl(overlap, n_win)], True, sums=work)
+    [start, start + n) on `axis`, the accumulation so far ends at `prev_end`.  One C call (aether_blend_link = scale
+    sums, cross-fade of the overlap, scaled copy of the new part; the scale stays on the device)."""
+    lib = _lib.require_device()
+    assert buf.dtype == torch.float64 and buf.dim() == 3 and buf.stride(2) == 1
+    wp, wf, w0, w1 = _v3(win)
+    e0, e1, e2 = win.shape
+    check(lib.aether_blend_link(buf.data_ptr(), buf.stride(0), buf.stride(1), wp, wf, w0, w1, e0, e1, e2, axis, start,
+                                prev_end, work.data_ptr(), current_stream()), "blend_link")
 
 
 def blend_chain(windows: Sequence[torch.Tensor], ranges: Sequence[Tuple[int, int]], axis: int,

@@ -330,6 +330,13 @@ int aether_blend_crossfade(double* dst, int64_t dst_s0, int64_t dst_s1, const vo
 int aether_scale_copy(double* dst, int64_t dst_s0, int64_t dst_s1, const void* src, int32_t src_is_f64, int64_t src_s0,
                       int64_t src_s1, double scale, const double* scale_sums, int32_t apply_scale, int64_t n0,
                       int64_t n1, int64_t n2, void* stream);
+/* One link of the blend chain in one call (SURVEY 8(b) `blend_tiles`): append window `win` (extents e0 x e1 x e2, fp32 or
+ * fp64) to the fp64 accumulation `buf` along `axis`; the window starts at index `start`, the accumulation so far ends at
+ * `prev_end` (overlap = prev_end - start >= 1).  Enqueues scale_reduce + blend_crossfade (in place on the overlap) +
+ * scale_copy (the new part); `work` as for aether_scale_reduce. */
+int aether_blend_link(double* buf, int64_t buf_s0, int64_t buf_s1, const void* win, int32_t win_is_f64, int64_t win_s0,
+                      int64_t win_s1, int64_t e0, int64_t e1, int64_t e2, int32_t axis, int64_t start, int64_t prev_end,
+                      void* work, void* stream);
 int aether_disparity_to_depth(double* dst, int64_t dst_s0, int64_t dst_s1, const void* src, int32_t src_is_f64,
                               int64_t src_s0, int64_t src_s1, int64_t n0, int64_t n1, int64_t n2, void* stream);
 
