@@ -14,6 +14,7 @@
 // size query and the real run can never disagree.  Everything is stream-ordered on one stream, so a block freed by
 // the host-side bookkeeping may be reused by a later launch immediately.
 #include <algorithm>
+#include <exception>
 #include <map>
 #include <new>
 #include <string>
@@ -264,6 +265,7 @@ struct Exec {
   // CogVideoXDownsample3D; consumes x
   Tn downsample(Tn x, const std::string& name, bool compress_time) {
     if (compress_time) {
+      if (x.T > 2 * IMap::kMax - 1) { run(AETHER_ERR_INVALID); drop(x); return Tn(); }   // frame batch larger than the by-value maps
       IMap ia, ib;
       int To;
       if (x.T % 2 == 1) {
@@ -290,6 +292,7 @@ struct Exec {
   Tn upsample(Tn x, const std::string& name, bool compress_time) {
     IMap tmap;
     int To;
+    if (2 * x.T > IMap::kMax) { run(AETHER_ERR_INVALID); drop(x); return Tn(); }
     if (compress_time && x.T > 1 && x.T % 2 == 1) {
       To = 1 + 2 * (x.T - 1);
       tmap.v[0] = 0;
@@ -301,7 +304,6 @@ struct Exec {
       To = x.T;
       for (int t = 0; t < To; ++t) tmap.v[t] = t;
     }
-    if (To > IMap::kMax) { run(AETHER_ERR_INVALID); return Tn(); }
     Tn up = make(To, 2 * x.H, 2 * x.W, x.C);
     ++launches;
     if (up.p && !dry() && ok()) run(upsample_nearest_imap(x.p, up.p, tmap, To, 2 * x.H, 2 * x.W, x.H, x.W, 2, 2, x.C, st));
@@ -488,9 +490,9 @@ int check_cfg(const AetherVaeConfig& c) {
 }
 
 // the shared body of the size query (dry) and the real calls
-int vae_run(const AetherVae* h, bool enc, const void* in, int64_t sC, int64_t sT, int64_t sH, int T, int H, int W, void* out,
+int vae_run_impl(const AetherVae* h, bool enc, const void* in, int64_t sC, int64_t sT, int64_t sH, int T, int H, int W, void* out,
             void* workspace, int64_t workspace_bytes, cudaStream_t st, bool dry, int64_t* peak, int64_t* launches,
-            int32_t* dims = nullptr) {
+            int32_t* dims) {
   const AetherVaeConfig& c = h->cfg;
   char* base = dry ? nullptr : reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023));
   const int64_t cap = dry ? 0 : workspace_bytes - (base - reinterpret_cast<char*>(workspace));
@@ -516,6 +518,18 @@ int vae_run(const AetherVae* h, bool enc, const void* in, int64_t sC, int64_t sT
   return ex.rc;
 }
 
+// The host-side bookkeeping uses std containers; nothing may propagate through the C boundary.
+int vae_run(const AetherVae* h, bool enc, const void* in, int64_t sC, int64_t sT, int64_t sH, int T, int H, int W, void* out,
+            void* workspace, int64_t workspace_bytes, cudaStream_t st, bool dry, int64_t* peak, int64_t* launches,
+            int32_t* dims = nullptr) {
+  try {
+    return vae_run_impl(h, enc, in, sC, sT, sH, T, H, W, out, workspace, workspace_bytes, st, dry, peak, launches, dims);
+  } catch (const std::exception& e) {
+    fprintf(stderr, "[aether_b200] vae: host-side failure: %s\n", e.what());
+    return AETHER_ERR_INVALID;
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -529,15 +543,20 @@ int aether_vae_create(const AetherVaeConfig* cfg, const AetherVaeParam* params, 
   AetherVae* h = new (std::nothrow) AetherVae;
   if (!h) return AETHER_ERR_INVALID;
   h->cfg = *cfg;
-  for (int i = 0; i < n_params; ++i) {
-    const AetherVaeParam& p = params[i];
-    if (!p.name || !p.data) { delete h; return AETHER_ERR_INVALID; }
-    const std::string name(p.name);
-    if (p.kind == 0) h->conv[name] = ConvP{p.data, p.bias, p.kt, p.kh, p.kw, p.cin, p.cout};
-    else if (p.kind == 1) h->norm[name] = NormP{reinterpret_cast<const float*>(p.data), p.bias};
-    else if (p.kind == 2) h->yb[name] = YbP{p.data, p.bias, p.cin, p.cout};
-    else if (p.kind == 3) h->yb_all = YbP{p.data, p.bias, 0, p.cout};
-    else { delete h; return AETHER_ERR_INVALID; }
+  try {
+    for (int i = 0; i < n_params; ++i) {
+      const AetherVaeParam& p = params[i];
+      if (!p.name || !p.data) { delete h; return AETHER_ERR_INVALID; }
+      const std::string name(p.name);
+      if (p.kind == 0) h->conv[name] = ConvP{p.data, p.bias, p.kt, p.kh, p.kw, p.cin, p.cout};
+      else if (p.kind == 1) h->norm[name] = NormP{reinterpret_cast<const float*>(p.data), p.bias};
+      else if (p.kind == 2) h->yb[name] = YbP{p.data, p.bias, p.cin, p.cout};
+      else if (p.kind == 3) h->yb_all = YbP{p.data, p.bias, 0, p.cout};
+      else { delete h; return AETHER_ERR_INVALID; }
+    }
+  } catch (const std::exception&) {
+    delete h;
+    return AETHER_ERR_INVALID;
   }
   *out = h;
   return AETHER_OK;

@@ -378,6 +378,22 @@ class TileParallelRun:
                                                                       self.world, self.root, self.group, self.device))
             if self.rank == self.root:
                 self._timed("blend_ms", lambda: [self.blend.push_tile(kk, dd) for kk, dd in got])
+            if j == 0 and self.world > 1 and self.root != tile_owner(0, self.world):
+                self._move_rgb0()
+
+    def _move_rgb0(self):
+        """The rgb the reference returns is tile 0's (:173-176, :265-266); when the blend rank is not its owner the
+        frames follow the disparity tile there, once."""
+        import torch.distributed as dist
+        owner = tile_owner(0, self.world)
+        if self.rank == owner:
+            r = torch.as_tensor(np.asarray(self.rgb0) if not isinstance(self.rgb0, torch.Tensor) else self.rgb0)
+            dist.send(r.to(device=self.device, dtype=torch.float32).contiguous(), self.root, group=self.group)
+            self.rgb0 = None
+        elif self.rank == self.root:
+            r = torch.empty(self.tile_shape + (3,), dtype=torch.float32, device=self.device)
+            dist.recv(r, owner, group=self.group)
+            self.rgb0 = r
 
     def collect_stats(self):
         """Fold the device timings recorded so far into `stats` (synchronises the device)."""

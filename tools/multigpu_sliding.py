@@ -27,7 +27,8 @@ def main():
     torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
     dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
     ok = True
-    for name in ("temporal", "horizontal", "vertical", "long"):
+    # the last pass puts the blend rank on the LAST rank (tile 0's rgb then follows the disparity tiles there)
+    for name, root in (("temporal", 0), ("horizontal", 0), ("vertical", 0), ("long", 0), ("long", world - 1)):
         g = np.load(ROOT / "tests" / "golden" / f"sliding_{name}.npz")
         t, h, w = g["thw"].tolist()
         obs = synthetic_long_clip(t, h, w)
@@ -40,7 +41,7 @@ def main():
         t0 = time.perf_counter()
         stats = {}
         rgb, disp = process_with_sliding_window(None, obs, 4, t, 3407, rank=rank, world_size=world, tile_fn=tile_fn,
-                                                result_on_all_ranks=True, stats=stats)
+                                                root=root, result_on_all_ranks=True, stats=stats)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         n_tiles = len(plan_windows(t, h, w, t).tiles)
@@ -49,7 +50,7 @@ def main():
                 and np.array_equal(subsample(rgb, (8, 32, 32, 1)), g["rgb_sub"])
                 and ran == list(range(rank, n_tiles, world)))
         ok = ok and good
-        print(f"[rank {rank}/{world}] sliding_{name}: tiles run here {ran} of {n_tiles}; matches reference golden: {good}; "
+        print(f"[rank {rank}/{world}] sliding_{name} (blend rank {root}): tiles run here {ran} of {n_tiles}; matches reference golden: {good}; "
               f"{dt:.2f} s; device-timed ms {dict((k, round(v, 2)) for k, v in stats.items())}", flush=True)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
