@@ -205,6 +205,13 @@ int aether_conv3d_bf16(const void* x, int32_t T_in, int32_t H_in, int32_t W_in, 
                        const float* bias, const void* resid, void* y, int32_t T_out, int32_t H_out, int32_t W_out,
                        int32_t Cout, int32_t kt, int32_t kh, int32_t kw, int32_t stride, int32_t pad_h, int32_t pad_w,
                        void* stream);
+/* Same operation, restricted to the one-CTA kernel.  aether_conv3d_bf16 runs Cout >= 128 on CTA pairs (tcgen05
+ * cta_group::2: two neighbouring output tiles share every weight tile); this entry is the pair kernel's bit-exact
+ * reference in the parity tests and the baseline of its A/B timing. */
+int aether_conv3d_bf16_1cta(const void* x, int32_t T_in, int32_t H_in, int32_t W_in, int32_t Cin, const void* w_packed,
+                            const float* bias, const void* resid, void* y, int32_t T_out, int32_t H_out, int32_t W_out,
+                            int32_t Cout, int32_t kt, int32_t kh, int32_t kw, int32_t stride, int32_t pad_h,
+                            int32_t pad_w, void* stream);
 /* GroupNorm statistics of x[N, C] (N = T*H*W): mean_rstd[2*G] = {mean_g, 1/sqrt(var_g + eps)}; deterministic.
  * workspace: aether_gn_workspace_floats(C) floats. */
 int64_t aether_gn_workspace_floats(int32_t C);

@@ -19,7 +19,7 @@ def _rel(got, ref):
     return (err.pow(2).mean().sqrt() / ref.pow(2).mean().sqrt().clamp_min(1e-12)).item(), err.abs().max().item()
 
 
-def _conv_call(x_cl, w, b, stride=1, pad=(1, 1), resid=None, out_hw=None):
+def _conv_call(x_cl, w, b, stride=1, pad=(1, 1), resid=None, out_hw=None, one_cta=False):
     """x_cl [T_in, H, W, Cin] (already time padded) ; w torch layout [Cout, Cin, kt, kh, kw]."""
     from aether_b200 import _lib
     from aether_b200._lib import check, current_stream, ptr
@@ -32,9 +32,10 @@ def _conv_call(x_cl, w, b, stride=1, pad=(1, 1), resid=None, out_hw=None):
     T_out = T_in - kt + 1
     Ho, Wo = out_hw or (H, W)
     y = torch.empty(T_out, Ho, Wo, cout, dtype=BF16, device=DEV)
-    check(_lib.require_device().aether_conv3d_bf16(ptr(x_cl), T_in, H, W, cin, ptr(wp), ptr(b), ptr(resid), ptr(y), T_out,
-                                                   Ho, Wo, cout, kt, kh, kw, stride, pad[0], pad[1], current_stream()),
-          "conv3d")
+    lib = _lib.require_device()
+    fn = lib.aether_conv3d_bf16_1cta if one_cta else lib.aether_conv3d_bf16
+    check(fn(ptr(x_cl), T_in, H, W, cin, ptr(wp), ptr(b), ptr(resid), ptr(y), T_out, Ho, Wo, cout, kt, kh, kw, stride,
+             pad[0], pad[1], current_stream()), "conv3d")
     return y
 
 
@@ -53,6 +54,31 @@ def test_conv3d_matches_torch(T, H, W, cin, cout, k):
     ref = F.conv3d(F.pad(xn, (p, p, p, p)), w, b)[0].permute(1, 2, 3, 0) + resid.float()
     rel, mx = _rel(y, ref)
     assert rel < 6e-3 and mx < 0.06, (rel, mx)
+
+
+@pytest.mark.parametrize("T,H,W,cin,cout,k,stride", [
+    (3, 12, 20, 64, 128, 3, 1),      # odd frames, even tile bands -> pairs along x ... whichever wastes least
+    (3, 24, 17, 128, 128, 3, 1),     # 3 frames x 3 row bands x 2 column bands
+    (5, 20, 40, 128, 256, 3, 1),     # every axis odd in tiles (5 x 3 x 3): one CTA of the last pair works on nothing
+    (2, 30, 45, 256, 512, 3, 1),     # two channel blocks of 256
+    (1, 9, 11, 128, 128, 1, 1),      # a single tile: the pair's second CTA is entirely out of range
+    (3, 24, 40, 128, 128, 3, 2),     # the stride-2 down-sampler
+    (9, 60, 90, 128, 128, 3, 1)])    # more tiles than CTA pairs: the persistent loop and the double-buffered accumulator
+def test_conv3d_cta_pair_is_bit_identical_to_one_cta(T, H, W, cin, cout, k, stride):
+    """aether_conv3d_bf16 runs Cout >= 128 on CTA pairs (cta_group::2); same K order, same epilogue -> same bits as the
+    one-CTA kernel, including tiles that hang over the last frame / row / column."""
+    g = torch.Generator(device=DEV).manual_seed(T * 1000 + H * 10 + W + cin + cout + stride)
+    kt = 1 if stride == 2 else k
+    x = torch.randn(T + kt - 1, H, W, cin, device=DEV, generator=g).to(BF16)
+    w = (torch.randn(cout, cin, kt, k, k, device=DEV, generator=g) / (cin * kt * k * k) ** 0.5).to(BF16).float()
+    b = torch.randn(cout, device=DEV, generator=g) * 0.1
+    out_hw = (H // 2, W // 2) if stride == 2 else (H, W)
+    resid = torch.randn(T, *out_hw, cout, device=DEV, generator=g).to(BF16)
+    pad = (0, 0) if stride == 2 else ((k - 1) // 2,) * 2
+    for _ in range(2):               # twice: barrier phases / accumulator buffers of a second launch
+        y2 = _conv_call(x, w, b, stride=stride, pad=pad, resid=resid, out_hw=out_hw)
+        y1 = _conv_call(x, w, b, stride=stride, pad=pad, resid=resid, out_hw=out_hw, one_cta=True)
+        assert torch.equal(y1, y2)
 
 
 def test_conv2d_stride2_downsample():
