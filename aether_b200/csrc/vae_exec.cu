@@ -2,7 +2,7 @@
 // .decode for one batch item -- 3 x 3 spatial tiling with the linear tile blends, frame batching with the causal
 // conv caches, every resnet / norm / resampling stage -- as ONE C call that only enqueues kernels on the caller's
 // stream: no host synchronisation, no allocation (scratch comes from the caller's workspace, sized by
-// aether_vae_workspace_bytes), no Python between the ~18 000 launches of a 41 x 480 x 720 decode.
+// aether_vae_workspace_bytes), no Python between the ~7 700 launches of a 41 x 480 x 720 decode.
 //
 // Replaces the device work behind  vae.encode(x).latent_dist  and  vae.decode(z).sample  (third-party diffusers
 // module; reference call sites aether/pipelines/aetherv1_pipeline_cogvideox.py:557-620, :931, :936; SURVEY.md 8(b)
@@ -107,6 +107,7 @@ struct Exec {
   cudaStream_t st;
   int rc = AETHER_OK;
   int64_t launches = 0;
+  unsigned* counter = nullptr;    // zeroed word for the one-launch GroupNorm statistics (head of the workspace)
   char* zyb_all = nullptr;        // [rows(zq), yb_all.n] conv_y | conv_b of EVERY decoder SpatialNorm for the current batch
 
   bool dry() const { return ar->dry(); }
@@ -154,7 +155,9 @@ struct Exec {
   }
 
   // ---- GroupNorm / SpatialNorm3D + SiLU of x into `out` (same shape; may be the tail of a time-padded buffer)
-  void norm(const Tn& x, const std::string& name, char* out, const Tn* zq) {
+  // `tail2` (optional): the last two frames of the result are ALSO written there (the next frame batch's conv cache)
+  void norm(const Tn& x, const std::string& name, char* out, const Tn* zq, char* tail2 = nullptr) {
+    const int64_t tail_from = tail2 ? int64_t(x.T - 2) * x.H * x.W : 0;
     const AetherVaeConfig& c = h->cfg;
     const int G = c.norm_num_groups;
     const bool spatial = zq != nullptr;
@@ -164,15 +167,15 @@ struct Exec {
     if (!ws) { run(AETHER_ERR_WORKSPACE); return; }
     float* partial = reinterpret_cast<float*>(ws);
     float* mr = reinterpret_cast<float*>(ws + ((gn_workspace_floats(x.C) * 4 + 255) & ~int64_t(255)));
-    launches += 2;
-    if (!dry() && ok()) run(gn_stats(x.p, x.rows(), x.C, G, eps, partial, mr, st));
+    ++launches;
+    if (!dry() && ok()) run(gn_stats(x.p, x.rows(), x.C, G, eps, partial, mr, counter, st));
     auto np = h->norm.find(spatial ? name + ".norm_layer" : name);
     if (np == h->norm.end()) { fprintf(stderr, "[aether_b200] vae: missing norm parameter %s\n", name.c_str()); run(AETHER_ERR_INVALID); ar->release(ws); return; }
     if (!spatial) {
       ++launches;
       if (!dry() && ok())
         run(gn_apply_imap(x.p, out, x.rows(), x.C, G, mr, np->second.g, np->second.b, nullptr, nullptr, 0, nullptr, x.H,
-                          x.W, 1, 1, 1, st));
+                          x.W, 1, 1, 1, tail2, tail_from, st));
       ar->release(ws);
       return;
     }
@@ -206,13 +209,14 @@ struct Exec {
     ++launches;
     if (!dry() && ok())
       run(gn_apply_imap(x.p, out, x.rows(), x.C, G, mr, np->second.g, np->second.b, zy, zy + int64_t(x.C) * 2, zld, &tmap,
-                        x.H, x.W, zq->H, zq->W, 1, st));
+                        x.H, x.W, zq->H, zq->W, 1, tail2, tail_from, st));
     if (zyb) ar->release(zyb);
     ar->release(ws);
   }
 
-  // ---- CogVideoXCausalConv3d time padding: [conv_cache] or [first frame] x 2 in front; returns the new cache (last 2)
-  Tn fill_time_pad(const Tn& buf, const Cache& cache, const std::string& name) {
+  // ---- CogVideoXCausalConv3d time padding: [conv_cache] or [first frame] x 2 in front; returns the new cache (last 2).
+  // `filled` = a cache buffer the producer of buf's payload has already written (norm's second destination).
+  Tn fill_time_pad(const Tn& buf, const Cache& cache, const std::string& name, const Tn* filled = nullptr) {
     const int64_t fb = buf.frame_bytes();
     auto it = cache.find(name);
     if (it != cache.end()) {
@@ -221,6 +225,7 @@ struct Exec {
       copy(buf.p, buf.p + 2 * fb, fb);
       copy(buf.p + fb, buf.p + 2 * fb, fb);
     }
+    if (filled) return *filled;
     Tn nc = make(2, buf.H, buf.W, buf.C);
     if (nc.p) copy(nc.p, buf.p + int64_t(buf.T - 2) * fb, 2 * fb);
     return nc;
@@ -242,8 +247,15 @@ struct Exec {
                const Tn* zq, const Tn* resid, char* dst = nullptr) {
     Tn buf = make(x.T + 2, x.H, x.W, x.C);
     if (!buf.p) return Tn();
-    norm(x, norm_name, buf.p + 2 * buf.frame_bytes(), zq);
-    nc[conv_name] = fill_time_pad(buf, cache, conv_name);
+    // with two or more frames in the batch the new cache (= the last two payload frames) is written by the norm kernel
+    // itself; a one-frame batch's cache also holds a padding frame and is copied out of the padded buffer afterwards
+    Tn ncache;
+    if (x.T >= 2) {
+      ncache = make(2, x.H, x.W, x.C);
+      if (!ncache.p) { drop(buf); return Tn(); }
+    }
+    norm(x, norm_name, buf.p + 2 * buf.frame_bytes(), zq, ncache.p);
+    nc[conv_name] = fill_time_pad(buf, cache, conv_name, ncache.p ? &ncache : nullptr);
     Tn y = conv(buf, conv_name, x.T, 1, 1, 1, resid, x.H, x.W, dst);
     drop(buf);
     return y;
@@ -496,9 +508,15 @@ int vae_run_impl(const AetherVae* h, bool enc, const void* in, int64_t sC, int64
   const AetherVaeConfig& c = h->cfg;
   char* base = dry ? nullptr : reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023));
   const int64_t cap = dry ? 0 : workspace_bytes - (base - reinterpret_cast<char*>(workspace));
-  if (!dry && (!workspace || cap <= 0)) return AETHER_ERR_WORKSPACE;
-  Arena ar(base, cap, dry);
+  constexpr int64_t kHead = 1024;           // head of the workspace: the GroupNorm statistics' arrival counter
+  if (!dry && (!workspace || cap <= kHead)) return AETHER_ERR_WORKSPACE;
+  Arena ar(dry ? nullptr : base + kHead, dry ? 0 : cap - kHead, dry);
   Exec ex{h, &ar, st};
+  ++ex.launches;
+  if (!dry) {
+    ex.counter = reinterpret_cast<unsigned*>(base);
+    if (cudaMemsetAsync(base, 0, size_t(kHead), st) != cudaSuccess) return AETHER_ERR_CUDA;
+  }
   const int C = enc ? c.in_channels : c.latent_channels;
   const int Cp = ((C + 7) / 8) * 8;
   Tn res = ex.tiled(enc, reinterpret_cast<const char*>(in), sC, sT, sH, C, Cp, T, H, W);
@@ -512,7 +530,7 @@ int vae_run_impl(const AetherVae* h, bool enc, const void* in, int64_t sC, int64
       if (!dry) ex.run(thwc_to_ncthw(res.p, out, c.out_channels, res.C, res.rows(), st));
     }
   }
-  if (peak) *peak = ar.peak() + 2048;
+  if (peak) *peak = ar.peak() + kHead + 2048;
   if (launches) *launches = ex.launches;
   if (ar.failed() && ex.rc == AETHER_OK) return AETHER_ERR_WORKSPACE;
   return ex.rc;

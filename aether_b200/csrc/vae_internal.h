@@ -20,12 +20,13 @@ int conv3d_bf16(const void* x, int T_in, int H_in, int W_in, int Cin, const void
 int gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int M, int N, int K,
               const float* bias, int epilogue, const float* gate_vid, const float* gate_txt, int64_t gate_bstride,
               int S, int St, int f16_from_col, cudaStream_t stream);
-int gn_stats(const void* x, int64_t N, int C, int G, float eps, float* workspace, float* mean_rstd,
+// `counter`: nullable zeroed device word (left zero); with it the statistics are ONE launch (see gn_partial_kernel)
+int gn_stats(const void* x, int64_t N, int C, int G, float eps, float* workspace, float* mean_rstd, unsigned* counter,
              cudaStream_t stream);
 int64_t gn_workspace_floats(int C);
 int gn_apply_imap(const void* x, void* y, int64_t N, int C, int G, const float* mean_rstd, const float* gamma,
                   const float* beta, const void* zy, const void* zb, int zld, const IMap* tmap, int H, int W, int hz,
-                  int wz, int silu, cudaStream_t stream);
+                  int wz, int silu, void* y2, int64_t y2_from, cudaStream_t stream);   // y2: rows >= y2_from also go there
 int upsample_nearest_imap(const void* in, void* out, const IMap& tmap, int To, int Ho, int Wo, int Hi, int Wi, int sy,
                           int sx, int C, cudaStream_t stream);
 int avgpool_time_imap(const void* in, void* out, const IMap& ia, const IMap& ib, int To, int64_t frame_elems,

@@ -21,16 +21,65 @@ __device__ __forceinline__ float bf16r(float x) { return __bfloat162float(__floa
 
 // ------------------------------------------------------------------------------------------------
 // GroupNorm statistics over x[N, C] (N = T*H*W positions): per-block partial sums of every 4-channel quad in
-// a fixed order, then a single-block fp64 finalize -> mean[G], rstd[G].  Deterministic (no atomics).
+// a fixed order, then an fp64 finalize per group -> mean[G], rstd[G].  Deterministic (no floating-point atomics).
 // Algorithmic bytes: N*C*2 read.
+// Shape of the reduction (round 2): at most ONE 1024-thread block per SM, so a group has <= #SM x (C/G/4) partials
+// (38 KB .. 150 KB in total) and a single block can finalize all groups in a few microseconds -- which lets the last
+// block to finish do it (one launch instead of two; the previous 8 x 256-thread blocks per SM left 0.3 - 1.2 MB of
+// partials, a 9 us stand-alone finalize launch per norm = 3 % of a VAE decode).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-gn_partial_kernel(const __nv_bfloat16* __restrict__ x, int64_t N, int C, float* __restrict__ partial) {
-  // thread layout: tpr = C/8 threads per row; rows advance by (256 / tpr) * gridDim.x
+constexpr int GN_THREADS = 1024;
+
+// Finalize of ONE group by ONE warp: the group's partials are read with eight independent L2 loads per lane and pass,
+// summed in fp64 per lane in index order and combined by a fixed shuffle tree.  Used by the fused tail of
+// gn_partial_kernel and by the stand-alone gn_finalize_kernel: same summation order -> identical bits.
+__device__ __forceinline__ void gn_finalize_group(const float* __restrict__ partial, int nblocks, int C, int G, int g,
+                                                  int lane, double count, float eps, float* __restrict__ mean_rstd) {
+  const int quads_per_group = (C / G) / 4;
+  const int n = nblocks * quads_per_group;
+  double s = 0.0, q = 0.0;
+  for (int i0 = lane; i0 < n; i0 += 32 * 8) {
+    float2 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + u * 32;
+      if (i < n) {
+        const int b = i / quads_per_group, k = i - b * quads_per_group;
+        // L2 (coherent) loads: in the fused kernel these values were written by other blocks of the same launch
+        v[u] = __ldcg(reinterpret_cast<const float2*>(partial + (int64_t(b) * (C / 4) + g * quads_per_group + k) * 2));
+      } else {
+        v[u] = make_float2(0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      s += v[u].x;
+      q += v[u].y;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  if (lane == 0) {
+    const double mean = s / count;
+    const double var = fmax(q / count - mean * mean, 0.0);
+    mean_rstd[2 * g] = float(mean);
+    mean_rstd[2 * g + 1] = float(1.0 / sqrt(var + double(eps)));
+  }
+}
+
+// `counter` (nullable): a zeroed device word.  With it the LAST block to finish (ticket from one integer atomicAdd) also
+// finalizes all G groups (one warp per group) and resets the counter; without it the caller launches gn_finalize_kernel.
+__global__ void __launch_bounds__(GN_THREADS)
+gn_partial_kernel(const __nv_bfloat16* __restrict__ x, int64_t N, int C, float* __restrict__ partial, int G, double count,
+                  float eps, float* __restrict__ mean_rstd, unsigned* __restrict__ counter) {
+  // thread layout: tpr = C/8 threads per row; rows advance by (GN_THREADS / tpr) * gridDim.x
   const int tpr = C / 8;
   const int lane_c = threadIdx.x % tpr;
   const int row_in_blk = threadIdx.x / tpr;
-  const int rows_per_blk = 256 / tpr;
+  const int rows_per_blk = GN_THREADS / tpr;
   float s[2] = {0.f, 0.f}, q[2] = {0.f, 0.f};
   const int64_t stride = int64_t(gridDim.x) * rows_per_blk;
   int64_t r = int64_t(blockIdx.x) * rows_per_blk + row_in_blk;
@@ -60,7 +109,7 @@ gn_partial_kernel(const __nv_bfloat16* __restrict__ x, int64_t N, int C, float* 
       s[1] += f[4 + j]; q[1] += f[4 + j] * f[4 + j];
     }
   }
-  extern __shared__ float red[];   // [256][4]
+  extern __shared__ float red[];   // [GN_THREADS][4]
   red[threadIdx.x * 4 + 0] = s[0]; red[threadIdx.x * 4 + 1] = q[0];
   red[threadIdx.x * 4 + 2] = s[1]; red[threadIdx.x * 4 + 3] = q[1];
   __syncthreads();
@@ -73,55 +122,26 @@ gn_partial_kernel(const __nv_bfloat16* __restrict__ x, int64_t N, int C, float* 
     float* out = partial + (int64_t(blockIdx.x) * (C / 4) + threadIdx.x * 2) * 2;
     out[0] = a0; out[1] = a1; out[2] = a2; out[3] = a3;
   }
+  if (counter == nullptr) return;
+  // ---- fused finalize: the last block to arrive sees every block's partials (release: fence + atomic; acquire: atomic + fence)
+  __shared__ unsigned ticket;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) ticket = atomicAdd(counter, 1u);
+  __syncthreads();
+  if (ticket != gridDim.x - 1) return;
+  __threadfence();
+  for (int g = threadIdx.x >> 5; g < G; g += GN_THREADS / 32)
+    gn_finalize_group(partial, int(gridDim.x), C, G, g, threadIdx.x & 31, count, eps, mean_rstd);
+  if (threadIdx.x == 0) *counter = 0u;     // ready for the next (stream-ordered) launch
 }
 
-// one BLOCK per group (grid = G): the partials of the group are read with every load independent of the others
-// (<= 8 per thread), summed in fp64 per thread in index order and combined by a fixed shuffle / shared-memory tree
-// (deterministic).  Round 2 profile: the previous single-block version (one warp per group, a dependent L2 load per
-// iteration) took 29 us per call -- 9-12 % of a VAE encode / decode; this one is launch-latency bound.
-__global__ void __launch_bounds__(128)
+// Stand-alone finalize (one block, one warp per group) -- the path of callers without a counter word.
+__global__ void __launch_bounds__(GN_THREADS)
 gn_finalize_kernel(const float* __restrict__ partial, int nblocks, int C, int G, double count, float eps,
                    float* __restrict__ mean_rstd) {
-  const int g = blockIdx.x;
-  const int quads_per_group = (C / G) / 4;
-  const int n = nblocks * quads_per_group;
-  double s = 0.0, q = 0.0;
-  for (int i0 = threadIdx.x; i0 < n; i0 += 128 * 8) {
-    float2 v[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int i = i0 + u * 128;
-      if (i < n) {
-        const int b = i / quads_per_group, k = i - b * quads_per_group;
-        v[u] = __ldg(reinterpret_cast<const float2*>(partial + (int64_t(b) * (C / 4) + g * quads_per_group + k) * 2));
-      } else {
-        v[u] = make_float2(0.f, 0.f);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      s += v[u].x;
-      q += v[u].y;
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    s += __shfl_xor_sync(0xffffffffu, s, o);
-    q += __shfl_xor_sync(0xffffffffu, q, o);
-  }
-  __shared__ double ss[4], sq[4];
-  if ((threadIdx.x & 31) == 0) {
-    ss[threadIdx.x >> 5] = s;
-    sq[threadIdx.x >> 5] = q;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const double S = (ss[0] + ss[1]) + (ss[2] + ss[3]), Q = (sq[0] + sq[1]) + (sq[2] + sq[3]);
-    const double mean = S / count;
-    const double var = fmax(Q / count - mean * mean, 0.0);
-    mean_rstd[2 * g] = float(mean);
-    mean_rstd[2 * g + 1] = float(1.0 / sqrt(var + double(eps)));
-  }
+  for (int g = threadIdx.x >> 5; g < G; g += GN_THREADS / 32)
+    gn_finalize_group(partial, nblocks, C, G, g, threadIdx.x & 31, count, eps, mean_rstd);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -144,6 +164,10 @@ struct GnApplyArgs {
   int H, W, hz, wz;
   int zld;                     // row stride (elements) of the zy / zb tables
   int silu;
+  // optional second destination for the rows >= y2_from (the last two frames = the causal conv's cache for the next
+  // frame batch, written here instead of by a separate device-to-device copy of what was just stored)
+  __nv_bfloat16* y2;
+  int64_t y2_from;
 };
 
 // Work layout: a thread owns ONE 8-channel vector of the row for the whole launch, so its group statistics and
@@ -210,7 +234,9 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyArgs a, cons
           f[j] = __fdividef(v, 1.0f + __expf(-v));
         }
       }
-      *reinterpret_cast<uint4*>(a.y + int64_t(r) * a.C + c0) = pack8v(f);
+      const uint4 o = pack8v(f);
+      *reinterpret_cast<uint4*>(a.y + int64_t(r) * a.C + c0) = o;
+      if (a.y2 != nullptr && int64_t(r) >= a.y2_from) *reinterpret_cast<uint4*>(a.y2 + (int64_t(r) - a.y2_from) * a.C + c0) = o;
     }
   }
 }
@@ -264,7 +290,9 @@ __global__ void __launch_bounds__(256) gn_apply_spatial_rx_kernel(const GnApplyA
           f[j] = __fdividef(v, 1.0f + __expf(-v));
         }
       }
-      *reinterpret_cast<uint4*>(a.y + (row0 + k) * a.C + c0) = pack8v(f);
+      const uint4 o = pack8v(f);
+      *reinterpret_cast<uint4*>(a.y + (row0 + k) * a.C + c0) = o;
+      if (a.y2 != nullptr && row0 + k >= a.y2_from) *reinterpret_cast<uint4*>(a.y2 + (row0 + k - a.y2_from) * a.C + c0) = o;
     }
   }
 }
@@ -419,12 +447,12 @@ copy_region_kernel(const uint4* __restrict__ src, int Hs, int Ws, uint4* __restr
 // ---- C++ entry points for the handle-level executor (vae_exec.cu): index maps by value, no device-side tables
 int gn_apply_imap(const void* x, void* y, int64_t N, int C, int G, const float* mean_rstd, const float* gamma,
                   const float* beta, const void* zy, const void* zb, int zld, const IMap* tmap, int H, int W, int hz,
-                  int wz, int silu, cudaStream_t stream) {
+                  int wz, int silu, void* y2, int64_t y2_from, cudaStream_t stream) {
   AETHER_CHECK_ARG(x && y && mean_rstd && gamma && beta && N > 0 && C % 8 == 0 && C % G == 0);
-  AETHER_CHECK_ARG(256 % (C / 8) == 0 && N < (int64_t(1) << 31) && (C / G) % 4 == 0);
+  AETHER_CHECK_ARG(256 % (C / 8) == 0 && N < (int64_t(1) << 31) && (C / G) % 4 == 0 && y2_from >= 0);
   GnApplyArgs a{reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y), N, C, G, mean_rstd, gamma,
                 beta, reinterpret_cast<const __nv_bfloat16*>(zy), reinterpret_cast<const __nv_bfloat16*>(zb), H, W, hz, wz,
-                zld > 0 ? zld : C, silu};
+                zld > 0 ? zld : C, silu, reinterpret_cast<__nv_bfloat16*>(y2), y2_from};
   const int rows_per_blk = 256 / (C / 8);
   int64_t blocks = ceil_div(N, int64_t(rows_per_blk) * 4);
   const int64_t cap = int64_t(num_sms()) * 8;
@@ -480,16 +508,17 @@ int copy_region_cl(const void* src, int Hs, int Ws, void* dst, int Hd, int Wd, i
 int64_t gn_workspace_floats(int C) { return int64_t(num_sms()) * 8 * (C / 4) * 2; }
 
 int gn_stats(const void* x, int64_t N, int C, int G, float eps, float* workspace, float* mean_rstd,
-             cudaStream_t stream) {
-  AETHER_CHECK_ARG(x && workspace && mean_rstd && N > 0 && C % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0 &&
+             unsigned* counter, cudaStream_t stream) {
+  AETHER_CHECK_ARG(x && workspace && mean_rstd && N > 0 && C % 8 == 0 && C <= 2048 && GN_THREADS % (C / 8) == 0 &&
                    C % G == 0 && (C / G) % 4 == 0);
-  const int rows_per_blk = 256 / (C / 8);
+  const int rows_per_blk = GN_THREADS / (C / 8);
   int nblocks = (int)ceil_div(N, rows_per_blk);
-  const int cap = num_sms() * 8;       // 8 resident blocks of 256 threads per SM
+  const int cap = num_sms();           // one resident 1024-thread block per SM
   if (nblocks > cap) nblocks = cap;
-  gn_partial_kernel<<<nblocks, 256, 256 * 4 * sizeof(float), stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), N, C,
-                                                                         workspace);
-  gn_finalize_kernel<<<G, 128, 0, stream>>>(workspace, nblocks, C, G, double(N) * (C / G), eps, mean_rstd);
+  const double count = double(N) * (C / G);
+  gn_partial_kernel<<<nblocks, GN_THREADS, GN_THREADS * 4 * sizeof(float), stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), N, C, workspace, G, count, eps, mean_rstd, counter);
+  if (counter == nullptr) gn_finalize_kernel<<<1, GN_THREADS, 0, stream>>>(workspace, nblocks, C, G, count, eps, mean_rstd);
   AETHER_CUDA_OK(cudaGetLastError());
   return AETHER_OK;
 }
@@ -526,7 +555,7 @@ int64_t aether_gn_workspace_floats(int32_t C) { return gn_workspace_floats(C); }
 
 int aether_gn_stats(const void* x, int64_t N, int32_t C, int32_t G, float eps, float* workspace, float* mean_rstd,
                     void* stream) {
-  return gn_stats(x, N, C, G, eps, workspace, mean_rstd, ST(stream));
+  return gn_stats(x, N, C, G, eps, workspace, mean_rstd, nullptr, ST(stream));
 }
 
 int aether_gn_apply(const void* x, void* y, int64_t N, int32_t C, int32_t G, const float* mean_rstd,
@@ -536,7 +565,8 @@ int aether_gn_apply(const void* x, void* y, int64_t N, int32_t C, int32_t G, con
   if ((zy == nullptr) != (zb == nullptr) || (zy && (!tmap || H <= 0 || W <= 0 || hz <= 0 || wz <= 0)))
     return AETHER_ERR_INVALID;
   if (256 % (C / 8) != 0 || N >= (int64_t(1) << 31) || (C / G) % 4 != 0) return AETHER_ERR_INVALID;
-  GnApplyArgs a{CBF(x), BF(y), N, C, G, mean_rstd, gamma, beta, CBF(zy), CBF(zb), H, W, hz, wz, zld > 0 ? zld : C, silu};
+  GnApplyArgs a{CBF(x), BF(y), N, C, G, mean_rstd, gamma, beta, CBF(zy), CBF(zb), H, W, hz, wz, zld > 0 ? zld : C, silu,
+                nullptr, 0};
   const int rows_per_blk = 256 / (C / 8);
   int64_t blocks = ceil_div(N, int64_t(rows_per_blk) * 4);
   const int64_t cap = int64_t(num_sms()) * 8;
