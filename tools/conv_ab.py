@@ -28,12 +28,13 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--json", default=None)
     ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--only", type=int, default=None, help="index into SHAPES (ncu captures)")
     args = ap.parse_args()
     lib = _lib.require_device()
     g = torch.Generator(device="cuda").manual_seed(0)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     rows = []
-    for name, T, H, W, cin, cout in SHAPES:
+    for name, T, H, W, cin, cout in (SHAPES if args.only is None else [SHAPES[args.only]]):
         x = torch.randn(T + 2, H, W, cin, device="cuda", generator=g).to(BF16)
         w = (torch.randn(cout, 27 * cin, device="cuda", generator=g) / (27 * cin) ** 0.5).to(BF16)
         b = torch.zeros(cout, device="cuda")
