@@ -67,7 +67,7 @@ def test_committed_bench_lines_follow_the_contract():
     """The bench lines committed under profiles/ (written by bench.py on a B200) carry every key of the measurement
     contract, with consistent values."""
     import json
-    line = json.loads((ROOT / "profiles" / "r2_bench_1gpu_k3.json").read_text())
+    line = json.loads((ROOT / "profiles" / "r2_bench_1gpu_final.json").read_text())
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
               "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline",
               "collective_ms", "blend_ms", "config5_4step", "exchange_blend_check", "gpu_library_baseline"):
