@@ -213,7 +213,7 @@ def run_reference(args):
 class SyntheticClip:
     """Stands in for the [1, T, H, W, 3] float64 array of launch_aether.prepare_input without holding T x 9.8 MB of
     host memory: crops are generated per tile, seeded by the tile position, either resident on the device (float32,
-    `value` rounds) or as host numpy float64 (`e2e` rounds)."""
+    `value` rounds) or as host numpy uint8 frames in page-locked memory (`e2e` rounds)."""
 
     def __init__(self, t, h, w, device):
         self.shape = (1, t, h, w, 3)
@@ -230,8 +230,11 @@ class SyntheticClip:
         key = (n, hh, ww)
         if self.host_mode:              # one host crop per shape, generated OUTSIDE the timed region (prepare_host)
             if ("host",) + key not in self._cache:
-                self._cache[("host",) + key] = np.random.default_rng(seed).integers(0, 256, (n, hh, ww, 3), dtype=np.uint8)
-            return self._cache[("host",) + key]
+                pinned = torch.empty((n, hh, ww, 3), dtype=torch.uint8).pin_memory()      # numpy view of pinned memory
+                arr = pinned.numpy()
+                arr[...] = np.random.default_rng(seed).integers(0, 256, (n, hh, ww, 3), dtype=np.uint8)
+                self._cache[("host",) + key] = (arr, pinned)
+            return self._cache[("host",) + key][0]
         if key not in self._cache:      # one resident crop per shape: "inputs already resident in HBM"
             g = torch.Generator(device=self.device).manual_seed(seed)
             self._cache[key] = torch.rand((n, hh, ww, 3), device=self.device, generator=g, dtype=torch.float32)
@@ -379,7 +382,7 @@ def run_product(args):
     run.finish_stats_reset()
     value = world * LATENT_FRAMES * args.steps * (tile_steps / DENOISE_STEPS) / (elapsed_ms / 1000.0)
 
-    # ---- e2e: the same round with host buffers (host float64 crop in, finalised blended frames out)
+    # ---- e2e: the same round with host buffers (host uint8 frames in pinned memory in, finalised blended frames out)
     clip.host_mode = True
     clip[0, 0:WINDOW, 0:480, 0:720, :]                      # generate the synthetic host crop before the timed region
     pinned = (torch.empty((WINDOW + STRIDE_T * world, CLIP_H, CLIP_W), dtype=torch.float64).pin_memory()
