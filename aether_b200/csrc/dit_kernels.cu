@@ -305,41 +305,67 @@ __device__ __forceinline__ void rope_vec(float (&f)[8], const float (&c)[8], con
   }
 }
 
+// TOK tokens per thread: all 2 * TOK activation vectors AND the tokens' cos / sin rows are requested before the first
+// use (round 2: the one-token version had 32 bytes in flight per thread, then a dependent 64-byte cos/sin fetch --
+// 56 % of the copy bandwidth); the LayerNorm affine parameters of the thread's 8 channels are fetched once.
+template <int TOK>
 __global__ void __launch_bounds__(128)
-qk_norm_rope_kernel(__nv_bfloat16* __restrict__ qkv, int S, int St, int H, const float* __restrict__ gq,
+qk_norm_rope_kernel(__nv_bfloat16* __restrict__ qkv, int total, int S, int St, int H, const float* __restrict__ gq,
                     const float* __restrict__ bq, const float* __restrict__ gk, const float* __restrict__ bk,
                     float eps, const float* __restrict__ cosb, const float* __restrict__ sinb) {
-  const int token = blockIdx.y;                     // b * S + s
-  const int s = token % S;
-  const int vec = blockIdx.x * 128 + threadIdx.x;   // 16-byte vector index inside the q span of the token
+  const int vec = blockIdx.x * 128 + threadIdx.x;   // 16-byte vector index inside the q span of a token
   if (vec >= H * 8) return;                         // whole warps only (H even)
   const int sub = vec & 7;                          // which 8 of the 64 elements
-  uint4* qp = reinterpret_cast<uint4*>(qkv + int64_t(token) * (3 * H * 64)) + vec;
-  uint4* kp = qp + H * 8;
-  const uint4 qraw = *qp, kraw = *kp;               // both loads issued before the first use
-  float fq[8], fk[8];
-  unpack8(qraw, fq);
-  unpack8(kraw, fk);
-  qk_norm_vec(fq, gq, bq, sub, eps);
-  qk_norm_vec(fk, gk, bk, sub, eps);
-  if (cosb != nullptr && s >= St) {
-    float c[8], sn[8];
-    load8(cosb + int64_t(s - St) * 64 + sub * 8, c);
-    load8(sinb + int64_t(s - St) * 64 + sub * 8, sn);
-    rope_vec(fq, c, sn);
-    rope_vec(fk, c, sn);
+  const int tok0 = blockIdx.y * TOK;                // token = b * S + s
+  uint4 qraw[TOK], kraw[TOK];
+  float c[TOK][8], sn[TOK][8];
+  bool rope[TOK];
+#pragma unroll
+  for (int i = 0; i < TOK; ++i) {
+    const int token = tok0 + i;
+    if (token < total) {
+      const uint4* qp = reinterpret_cast<const uint4*>(qkv + int64_t(token) * (3 * H * 64)) + vec;
+      qraw[i] = qp[0];
+      kraw[i] = qp[H * 8];
+    }
   }
-  *qp = pack8(fq);
-  *kp = pack8(fk);
+#pragma unroll
+  for (int i = 0; i < TOK; ++i) {
+    const int token = tok0 + i;
+    const int s = token % S;
+    rope[i] = cosb != nullptr && token < total && s >= St;
+    if (rope[i]) {
+      load8(cosb + int64_t(s - St) * 64 + sub * 8, c[i]);
+      load8(sinb + int64_t(s - St) * 64 + sub * 8, sn[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < TOK; ++i) {
+    const int token = tok0 + i;
+    if (token >= total) break;                      // uniform per block.y: shuffles below stay converged
+    float fq[8], fk[8];
+    unpack8(qraw[i], fq);
+    unpack8(kraw[i], fk);
+    qk_norm_vec(fq, gq, bq, sub, eps);
+    qk_norm_vec(fk, gk, bk, sub, eps);
+    if (rope[i]) {
+      rope_vec(fq, c[i], sn[i]);
+      rope_vec(fk, c[i], sn[i]);
+    }
+    uint4* qp = reinterpret_cast<uint4*>(qkv + int64_t(token) * (3 * H * 64)) + vec;
+    qp[0] = pack8(fq);
+    qp[H * 8] = pack8(fk);
+  }
 }
 
 int qk_norm_rope(void* qkv, int B, int S, int St, int H, const float* gq, const float* bq, const float* gk,
                  const float* bk, float eps, const float* cosb, const float* sinb, cudaStream_t stream) {
   AETHER_CHECK_ARG(B > 0 && S > 0 && H > 0 && gq && bq && gk && bk);
   AETHER_CHECK_ARG((cosb == nullptr) == (sinb == nullptr));
-  dim3 grid((unsigned)ceil_div(H * 8, 128), (unsigned)(B * S));
-  qk_norm_rope_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<__nv_bfloat16*>(qkv), S, St, H, gq, bq, gk, bk, eps,
-                                                cosb, sinb);
+  constexpr int TOK = 2;
+  dim3 grid((unsigned)ceil_div(H * 8, 128), (unsigned)ceil_div(B * S, TOK));
+  qk_norm_rope_kernel<TOK><<<grid, 128, 0, stream>>>(reinterpret_cast<__nv_bfloat16*>(qkv), B * S, S, St, H, gq, bq, gk,
+                                                      bk, eps, cosb, sinb);
   AETHER_CUDA_OK(cudaGetLastError());
   return AETHER_OK;
 }
