@@ -1,6 +1,8 @@
 #!/bin/bash
-# Round-2 GPU call I (1 GPU): attention experiments -- mode 6 (lazy max), 7 (packed f32x2 math), 8 (both) vs mode 5:
-# parity, isolated timing, in-step timing (development rounds of 10 denoise steps).
+# Round-2 GPU call I (1 GPU), kept as the record of how the attention experiments were run: experimental modes 6 (lazy
+# max), 7 (packed f32x2 math), 8 (both) vs mode 5 -- parity, isolated timing, in-step timing (development rounds of 10
+# denoise steps).  The packed math became mode 5 and the experimental ids were removed again (git history), so today the
+# dispatcher rejects 6 / 7 and this script only reproduces the mode-5 rows.
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_kernels_gpu.py tests/test_fullsize_properties_gpu.py tests/test_vae_gpu.py -m gpu -q \
     -k "attention or native or vae_decode" --timeout 600 -p no:cacheprovider > gpurun_out/r2i_pytest.log 2>&1
