@@ -450,6 +450,10 @@ def run_product(args):
                       "matches_rtol_2e-6": ok}
 
     if rank == 0:
+        try:          # launches inside the native VAE calls (each counted once in _lib.CALLS): 1 encode + 2 decodes per tile
+            vae_extra = 0 if vae.per_op else ((vae.launches(0, WINDOW, 480, 720) - 1) + 2 * (vae.launches(1, LATENT_FRAMES, LAT_H, LAT_W) - 1))
+        except Exception:
+            vae_extra = 0
         peak, peak_src = _peaks()
         flop = 4.0 * 1 * HEADS * float(S_TOKENS) ** 2 * 64
         avg_ms = attn_ms / max(attn_n, 1)
@@ -469,7 +473,10 @@ def run_product(args):
             "collective_ms": per_round("collective_ms"), "blend_ms": per_round("blend_ms"),
             "tile_ms": per_round("tile_ms"),
             "collective_note": "per round on the blend rank; includes waiting for the slowest rank's tile of the round",
-            "gpu_launches": int(round(calls_per_round + tile_steps * (model.launches_per_forward(1) - 1))) * args.steps,
+            "gpu_launches": int(round(calls_per_round + tile_steps * (model.launches_per_forward(1) - 1) + vae_extra)) * args.steps,
+            "gpu_launches_note": "per round: C-ABI calls counted live + (kernels per DiT forward - 1) x denoise steps + the kernels "
+                                 "and device copies the three native VAE calls enqueue beyond their own call (dry-run count of "
+                                 "aether_vae_encode / aether_vae_decode); x timed rounds",
             "clocks": clocks,
             "roofline": {"kernel": f"aether_attention_bf16 mode {int(model.attention_fp16_pv)} (tcgen05)",
                          "bound": "tensor", "achieved": achieved, "peak": peak,
