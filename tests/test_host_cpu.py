@@ -97,6 +97,26 @@ def test_committed_bench_lines_follow_the_contract():
     assert ref["e2e"]["h2d_bytes_per_step"] == 0 and ref["cpu_baseline"]["value"] == ref["value"]
 
 
+def test_committed_multi_gpu_line_and_launch_shares_are_consistent(tmp_path):
+    """The 8-GPU line is the same command at N = 8 (weak scaling: 8 tiles per round); the launch-share table under
+    profiles/ is what tools/launch_shares.py derives from the committed ncu launch list."""
+    import json
+    import subprocess
+    import sys
+    last = lambda name: json.loads((ROOT / "profiles" / name).read_text().strip().splitlines()[-1])
+    one, eight = last("r2_bench_1gpu_final.json"), last("r2_bench_8gpu_final.json")      # (stdout of that run also holds NCCL's banner)
+    assert eight["n_gpus"] == 8 and eight["metric"] == one["metric"] and eight["scaling"] == "weak"
+    assert eight["config"]["denoise_steps"] == 50 and eight["config"]["tiles_per_round"] == 8
+    assert eight["value"] == pytest.approx(8 * 11 / (eight["ms_per_step"] / 1000.0), rel=1e-6)
+    assert eight["exchange_blend_check"] == {**one["exchange_blend_check"], "world_size": 8}
+    assert (eight["collective_ms"] + eight["blend_ms"]) < 0.02 * eight["ms_per_step"]      # VERDICT r1: < 2 % of the round
+    assert 0.85 < eight["value"] / (8 * one["value"]) < 1.15                                # different boxes, +-3 % clocks
+    out = tmp_path / "shares.md"
+    subprocess.run([sys.executable, str(ROOT / "tools" / "launch_shares.py"), str(ROOT / "profiles" / "r2_bench_launches.csv"),
+                    str(out), str(ROOT / "profiles" / "r2_bench_1gpu_final.json")], check=True, capture_output=True)
+    assert out.read_text() == (ROOT / "profiles" / "r2_bench_launch_shares.md").read_text()
+
+
 def test_library_has_no_libcuda_dependency():
     """The .so must load on a machine without the CUDA driver (driver entry points are resolved at run time)."""
     import subprocess
